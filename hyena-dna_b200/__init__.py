@@ -1,0 +1,14 @@
+"""hyena_b200 -- Blackwell-native (sm_100a) Hyena long-convolution operator.
+
+Drop-in for the HyenaOperator / HyenaFilter / fftconv surface of HazyResearch/hyena-dna
+(src/models/sequence/hyena.py, src/ops/fftconv.py, csrc/fftconv).  Import as ``hyena_dna_b200``.
+"""
+from ._lib import HyenaB200Error, LIB_PATH, build, launch_count  # noqa: F401
+from .hyena import (ExponentialModulation, HyenaFilter, HyenaOperator, OptimModule,  # noqa: F401
+                    PositionalEmbedding, Sin)
+from .fftconv import FFTConvFunc, fftconv_bwd, fftconv_func, fftconv_fwd  # noqa: F401
+from . import distributed, ops, registry  # noqa: F401
+
+__all__ = ["HyenaOperator", "HyenaFilter", "PositionalEmbedding", "ExponentialModulation", "Sin", "OptimModule",
+           "fftconv_func", "FFTConvFunc", "fftconv_fwd", "fftconv_bwd", "registry", "distributed", "ops",
+           "build", "launch_count", "HyenaB200Error", "LIB_PATH"]

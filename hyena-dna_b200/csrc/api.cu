@@ -1,0 +1,329 @@
+// C ABI of libhyena_b200.so (include/hyena_b200.h): argument checks, workspace carving, row-group
+// scheduling of the three FFT passes.  No torch types; PyTorch hands in raw device pointers.
+#include <atomic>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/hyena_b200.h"
+#include "launch.h"
+
+namespace hy {
+
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+#define HY_CUDA(expr)                                                                        \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) return fail("%s failed: %s", #expr, cudaGetErrorString(_e));      \
+  } while (0)
+#define HY_CHECK(cond, ...) \
+  do { if (!(cond)) return fail(__VA_ARGS__); } while (0)
+
+// ---------------------------------------------------------------- per-device twiddle tables
+struct DevTables { float2* tw1024 = nullptr; float2* twlo = nullptr; };
+static DevTables g_tables[64];
+static std::mutex g_mu;
+
+static int get_twiddles(cudaStream_t s, Twiddles* out) {
+  int dev = -1;
+  HY_CUDA(cudaGetDevice(&dev));
+  HY_CHECK(dev >= 0 && dev < 64, "unsupported device ordinal %d", dev);
+  std::lock_guard<std::mutex> lk(g_mu);
+  DevTables& t = g_tables[dev];
+  if (!t.tw1024) {
+    float2* mem = nullptr;
+    HY_CUDA(cudaMalloc(&mem, 2 * 1024 * sizeof(float2)));
+    HY_CUDA(launch_twiddle_init(mem, mem + 1024, s));
+    // later calls may come on other streams: make the table visible to all of them
+    HY_CUDA(cudaStreamSynchronize(s));
+    t.tw1024 = mem;
+    t.twlo = mem + 1024;
+  }
+  out->tw1024 = t.tw1024;
+  out->twlo = t.twlo;
+  return 0;
+}
+
+// ---------------------------------------------------------------- geometry
+static int log_m1_for(int L) {        // M = 1024 * 2^logM1 >= L
+  int lg = 0;
+  while (((size_t)kM2 << lg) < (size_t)L) ++lg;
+  return lg;
+}
+static size_t row_bytes(int L) { return ((size_t)kM2 << log_m1_for(L)) * sizeof(float2); }
+
+static size_t group_budget_bytes() {
+  // scratch kept in flight per launch group; sized to stay resident in B200's 126 MB L2
+  static size_t v = 0;
+  if (!v) {
+    const char* e = getenv("HYENA_B200_GROUP_MB");
+    long mb = e ? atol(e) : 32;
+    if (mb < 1) mb = 1;
+    v = (size_t)mb << 20;
+  }
+  return v;
+}
+
+// channels per group given the bytes available for ONE scratch array holding all batches of a channel
+static int channels_per_group(size_t bytes_for_A, int B, int D, int L) {
+  size_t per_ch = row_bytes(L) * (size_t)B;
+  size_t n = bytes_for_A / per_ch;
+  if (n > (size_t)D) n = D;
+  size_t cap = 65535 / (size_t)B;
+  if (n > cap) n = cap;
+  return (int)n;
+}
+
+static bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
+
+struct Carve { float2* A; float2* A2; float2* A3; int nch; };
+
+// backward needs A and A2 (B rows per channel each) and A3 (1 row per channel)
+static int carve(void* ws, size_t ws_bytes, int B, int D, int L, bool backward, Carve* c) {
+  HY_CHECK(ws != nullptr && aligned8(ws), "workspace must be a non-null 8-byte aligned device pointer");
+  const size_t rb = row_bytes(L);
+  const size_t per_ch = backward ? rb * (2 * (size_t)B + 1) : rb * (size_t)B;
+  HY_CHECK(ws_bytes >= per_ch, "workspace too small: %zu bytes given, %zu needed (hyena_b200_workspace_min_bytes)",
+           ws_bytes, per_ch);
+  size_t n = ws_bytes / per_ch;
+  if (n > (size_t)D) n = D;
+  size_t cap = 65535 / (size_t)B;
+  if (n > cap) n = cap;
+  c->nch = (int)n;
+  c->A = reinterpret_cast<float2*>(ws);
+  c->A2 = backward ? c->A + (rb / sizeof(float2)) * (size_t)B * n : nullptr;
+  c->A3 = backward ? c->A2 + (rb / sizeof(float2)) * (size_t)B * n : nullptr;
+  return 0;
+}
+
+static int check_shape(int B, int D, int L) {
+  HY_CHECK(B >= 1 && D >= 1 && L >= 1, "bad shape B=%d D=%d L=%d", B, D, L);
+  HY_CHECK(L <= (1 << 20), "sequence length %d exceeds the supported maximum %d", L, 1 << 20);
+  HY_CHECK(B <= 65535, "batch %d too large", B);
+  return 0;
+}
+
+static PassArgs base_args(int B, int D, int L, const Twiddles& T) {
+  PassArgs a;
+  memset(&a, 0, sizeof(a));
+  a.L = L; a.logM1 = log_m1_for(L); a.B = B; a.D = D; a.T = T;
+  a.scale = 1.0f / (4.0f * (float)((size_t)kM2 << a.logM1));
+  return a;
+}
+
+}  // namespace hy
+
+using namespace hy;
+
+extern "C" {
+
+HY_API int hyena_b200_abi_version(void) { return HYENA_B200_ABI_VERSION; }
+HY_API const char* hyena_b200_last_error(void) { return g_err; }
+HY_API unsigned long long hyena_b200_launch_count(void) { return g_launches.load(); }
+HY_API int hyena_b200_max_seqlen(void) { return 1 << 20; }
+
+HY_API size_t hyena_b200_spectrum_elems(int L) { return L < 1 ? 0 : ((size_t)kM2 << log_m1_for(L)); }
+
+HY_API size_t hyena_b200_workspace_min_bytes(int B, int D, int L, int backward) {
+  (void)D;
+  if (B < 1 || L < 1) return 0;
+  return backward ? row_bytes(L) * (2 * (size_t)B + 1) : row_bytes(L) * (size_t)B;
+}
+
+HY_API size_t hyena_b200_workspace_bytes(int B, int D, int L, int backward) {
+  if (B < 1 || L < 1 || D < 1) return 0;
+  int nch = channels_per_group(group_budget_bytes(), B, D, L);
+  if (nch < 1) nch = 1;
+  return hyena_b200_workspace_min_bytes(B, D, L, backward) * (size_t)nch;
+}
+
+static int fill_filter_params(FilterParams* P, const float* z, int z_stride, const float* t, const float* W0,
+                              const float* b0, const float* W1, const float* b1, const float* W2, const float* b2,
+                              const float* W3, const float* freq, const float* deltas, float shift, int modulate,
+                              int L, int E, int N, int D) {
+  HY_CHECK(N == kFN, "filter_order %d not supported (this build handles %d)", N, kFN);
+  HY_CHECK(E >= 3 && E < kMaxE && (E & 1), "emb_dim %d not supported (odd, 3..%d)", E, kMaxE - 1);
+  HY_CHECK(L >= 1 && D >= 1, "bad filter shape L=%d D=%d", L, D);
+  HY_CHECK(z && t && W0 && b0 && W1 && b1 && W2 && b2 && W3 && freq && deltas, "null filter parameter");
+  HY_CHECK((reinterpret_cast<uintptr_t>(W3) & 15u) == 0, "W3 must be 16-byte aligned");
+  P->z = z; P->t = t; P->W0 = W0; P->b0 = b0; P->W1 = W1; P->b1 = b1; P->W2 = W2; P->b2 = b2; P->W3 = W3;
+  P->freq = freq; P->deltas = deltas; P->shift = shift; P->modulate = modulate;
+  P->L = L; P->E = E; P->D = D; P->z_stride = z_stride;
+  return 0;
+}
+
+HY_API int hyena_b200_filter_fwd(const float* z, int z_stride, const float* t, const float* W0, const float* b0,
+                          const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
+                          const float* freq, const float* deltas, float shift, int modulate, int L, int E, int N,
+                          int D, float* k_out, void* stream) {
+  FilterParams P;
+  if (fill_filter_params(&P, z, z_stride, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, shift, modulate, L, E, N, D))
+    return 1;
+  HY_CHECK(k_out, "null output");
+  HY_CUDA(launch_filter_fwd(P, k_out, (cudaStream_t)stream));
+  return 0;
+}
+
+HY_API int hyena_b200_filter_bwd(const float* z, int z_stride, const float* t, const float* W0, const float* b0,
+                          const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
+                          const float* freq, const float* deltas, float shift, int modulate, int L, int E, int N,
+                          int D, const float* dk, float* dW0, float* db0, float* dW1, float* db1, float* dW2,
+                          float* db2, float* dW3, float* dfreq, float* dz, int dz_stride, void* stream) {
+  FilterParams P;
+  if (fill_filter_params(&P, z, z_stride, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, shift, modulate, L, E, N, D))
+    return 1;
+  HY_CHECK(dk && dW0 && db0 && dW1 && db1 && dW2 && db2 && dW3 && dfreq, "null gradient pointer");
+  FilterGrads G{dW0, db0, dW1, db1, dW2, db2, dW3, dfreq, dz, dz_stride};
+  HY_CUDA(launch_filter_bwd(P, dk, G, (cudaStream_t)stream));
+  return 0;
+}
+
+HY_API int hyena_b200_filter_spectrum(const float* k, float* kspec, int D, int L, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  if (check_shape(1, D, L)) return 1;
+  HY_CHECK(k && kspec && aligned8(kspec), "null or misaligned pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  Twiddles T;
+  if (get_twiddles(s, &T)) return 1;
+  Carve c;
+  if (carve(workspace, workspace_bytes, 1, D, L, false, &c)) return 1;
+  PassArgs a = base_args(1, D, L, T);
+  a.A = c.A; a.src = k; a.kspec_out = reinterpret_cast<float2*>(kspec);
+  a.vec = ((L & 1) == 0) && aligned8(k);
+  for (int c0 = 0; c0 < D; c0 += c.nch) {
+    const int n = (D - c0 < c.nch) ? D - c0 : c.nch;
+    a.c0 = c0;
+    HY_CUDA(launch_col_fwd(COL_FILTER, a, n, s));
+    HY_CUDA(launch_row_pass(ROW_FILTER, a, n, s));
+  }
+  return 0;
+}
+
+HY_API int hyena_b200_core_fwd(const float* p, const float* in_bias, const float* sw, const float* sb, const float* kspec,
+                        const float* fbias, float* y_pre, float* c_save, int B, int D, int L, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  if (check_shape(B, D, L)) return 1;
+  HY_CHECK(p && sw && sb && kspec && fbias && y_pre, "null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  Twiddles T;
+  if (get_twiddles(s, &T)) return 1;
+  Carve c;
+  if (carve(workspace, workspace_bytes, B, D, L, false, &c)) return 1;
+  PassArgs a = base_args(B, D, L, T);
+  a.A = c.A; a.kspec = reinterpret_cast<const float2*>(kspec);
+  a.p = p; a.in_bias = in_bias; a.sw = sw; a.sb = sb; a.fbias = fbias; a.out = y_pre; a.out2 = c_save;
+  a.vec = ((L & 1) == 0) && aligned8(p) && aligned8(y_pre) && (!c_save || aligned8(c_save));
+  for (int c0 = 0; c0 < D; c0 += c.nch) {
+    const int n = (D - c0 < c.nch) ? D - c0 : c.nch;
+    a.c0 = c0;
+    HY_CUDA(launch_col_fwd(COL_GATE, a, n * B, s));
+    HY_CUDA(launch_row_pass(ROW_CONV_FWD, a, n * B, s));
+    HY_CUDA(launch_col_inv(INV_CONV_FWD, a, n * B, s));
+  }
+  return 0;
+}
+
+HY_API int hyena_b200_core_bwd(const float* dy_pre, const float* p, const float* in_bias, const float* sw, const float* sb,
+                        const float* kspec, const float* fbias, const float* c_saved, float* dp, float* dk,
+                        float* dsw, float* dsb, float* dfbias, float* d_in_bias, float* ds_scratch, int B, int D,
+                        int L, void* workspace, size_t workspace_bytes, void* stream) {
+  if (check_shape(B, D, L)) return 1;
+  HY_CHECK(dy_pre && p && sw && sb && kspec && fbias && c_saved && dp && dk && dsw && dsb && dfbias && ds_scratch,
+           "null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  Twiddles T;
+  if (get_twiddles(s, &T)) return 1;
+  Carve c;
+  if (carve(workspace, workspace_bytes, B, D, L, true, &c)) return 1;
+  PassArgs a = base_args(B, D, L, T);
+  a.kspec = reinterpret_cast<const float2*>(kspec);
+  a.p = p; a.in_bias = in_bias; a.sw = sw; a.sb = sb; a.fbias = fbias;
+  a.vec = ((L & 1) == 0) && aligned8(p) && aligned8(dy_pre) && aligned8(c_saved) && aligned8(dk) &&
+          aligned8(ds_scratch) && aligned8(dp);
+  for (int c0 = 0; c0 < D; c0 += c.nch) {
+    const int n = (D - c0 < c.nch) ? D - c0 : c.nch;
+    a.c0 = c0; a.B = B;
+    a.A2 = c.A2; a.A3 = c.A3;
+    a.A = c.A; a.src = dy_pre;
+    HY_CUDA(launch_col_fwd(COL_DC, a, n * B, s));        // A  <- columns of dc = dy_pre * x0
+    a.A = c.A2;
+    HY_CUDA(launch_col_fwd(COL_GATE, a, n * B, s));      // A2 <- columns of g = v * x1 (recomputed)
+    a.A = c.A;
+    HY_CUDA(launch_row_pass(ROW_CONV_BWD, a, n, s));     // A <- rows of dg, A3 <- rows of dk
+    a.src = dy_pre; a.src2 = c_saved; a.out2 = ds_scratch; a.red = dfbias;
+    HY_CUDA(launch_col_inv(INV_BWD_DG, a, n * B, s));
+    a.B = 1; a.out = dk;
+    HY_CUDA(launch_col_inv(INV_DK, a, n, s));
+  }
+  ShortBwdArgs sa{ds_scratch, p, in_bias, sw, dp, dsw, dsb, d_in_bias, L, 3 * D, a.vec};
+  HY_CUDA(launch_short_bwd(sa, B, s));
+  return 0;
+}
+
+HY_API int hyena_b200_fftconv_fwd(const float* u, const float* kspec, const float* Dvec, float* out, int B, int H, int L,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  if (check_shape(B, H, L)) return 1;
+  HY_CHECK(u && kspec && Dvec && out, "null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  Twiddles T;
+  if (get_twiddles(s, &T)) return 1;
+  Carve c;
+  if (carve(workspace, workspace_bytes, B, H, L, false, &c)) return 1;
+  PassArgs a = base_args(B, H, L, T);
+  a.A = c.A; a.kspec = reinterpret_cast<const float2*>(kspec);
+  a.src = u; a.fbias = Dvec; a.out = out;
+  a.vec = ((L & 1) == 0) && aligned8(u) && aligned8(out);
+  for (int c0 = 0; c0 < H; c0 += c.nch) {
+    const int n = (H - c0 < c.nch) ? H - c0 : c.nch;
+    a.c0 = c0;
+    HY_CUDA(launch_col_fwd(COL_PLAIN, a, n * B, s));
+    HY_CUDA(launch_row_pass(ROW_CONV_FWD, a, n * B, s));
+    HY_CUDA(launch_col_inv(INV_PLAIN_FWD, a, n * B, s));
+  }
+  return 0;
+}
+
+HY_API int hyena_b200_fftconv_bwd(const float* dout, const float* u, const float* kspec, const float* Dvec, float* du,
+                           float* dk, float* dD, int B, int H, int L, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  if (check_shape(B, H, L)) return 1;
+  HY_CHECK(dout && u && kspec && Dvec && du && dk && dD, "null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  Twiddles T;
+  if (get_twiddles(s, &T)) return 1;
+  Carve c;
+  if (carve(workspace, workspace_bytes, B, H, L, true, &c)) return 1;
+  PassArgs a = base_args(B, H, L, T);
+  a.kspec = reinterpret_cast<const float2*>(kspec);
+  a.fbias = Dvec;
+  a.vec = ((L & 1) == 0) && aligned8(u) && aligned8(dout) && aligned8(du) && aligned8(dk);
+  for (int c0 = 0; c0 < H; c0 += c.nch) {
+    const int n = (H - c0 < c.nch) ? H - c0 : c.nch;
+    a.c0 = c0; a.B = B;
+    a.A2 = c.A2; a.A3 = c.A3;
+    a.A = c.A; a.src = dout;
+    HY_CUDA(launch_col_fwd(COL_PLAIN, a, n * B, s));
+    a.A = c.A2; a.src = u;
+    HY_CUDA(launch_col_fwd(COL_PLAIN, a, n * B, s));
+    a.A = c.A;
+    HY_CUDA(launch_row_pass(ROW_CONV_BWD, a, n, s));
+    a.src = u; a.src2 = dout; a.out = du; a.red = dD;
+    HY_CUDA(launch_col_inv(INV_PLAIN_BWD, a, n * B, s));
+    a.B = 1; a.out = dk;
+    HY_CUDA(launch_col_inv(INV_DK, a, n, s));
+  }
+  return 0;
+}
+
+}  // extern "C"

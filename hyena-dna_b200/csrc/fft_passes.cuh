@@ -1,0 +1,532 @@
+// The three passes of the long real-FFT convolution (see DESIGN.md "Kernels").
+//
+// A (batch, channel) row of L real samples is packed as z[m] = x[2m] + i x[2m+1] and zero padded
+// to M = M1 * 1024 complex points (n = 2M >= 2L).  M is split as m = 1024*m1 + m2, k = k1 + M1*k2:
+//
+//   pass 1  col_fwd : for every column m2, FFT over m1 (length M1) and twiddle W_M^{m2 k1}
+//                     -> scratch A[row][k1][m2]                      (input side fused in)
+//   pass 2  row_pass: for every k1, FFT over m2 (length 1024) -> spectrum Z[k1][k2];
+//                     pointwise product with the filter spectrum (pairs bin k with bin M-k),
+//                     inverse FFT over k2, conj twiddle -> scratch A[row][k1][m2] in place
+//   pass 3  col_inv : for every column m2, inverse FFT over k1 -> z'[m1][m2] = y[2m] + i y[2m+1]
+//                     (output side fused in)
+//
+// All spectra are kept in "[k1][k2]" order; nothing is ever transposed in HBM.
+#pragma once
+#include "fft_radix.cuh"
+
+namespace hy {
+
+constexpr int kM2 = 1024;       // row FFT length (fixed)
+constexpr int kLogM2 = 10;
+
+// ------------------------------------------------------------------------------------------------
+// short depthwise filter + gates (reference: src/models/sequence/hyena.py:363-369, :394, :420, :432)
+// ------------------------------------------------------------------------------------------------
+struct Taps { float w0, w1, w2, b, ib; };
+
+__device__ __forceinline__ Taps load_taps(const float* sw, const float* sb, const float* in_bias, int ch) {
+  Taps k;
+  k.w0 = __ldg(sw + 3 * ch + 0); k.w1 = __ldg(sw + 3 * ch + 1); k.w2 = __ldg(sw + 3 * ch + 2);
+  k.b = __ldg(sb + ch);
+  k.ib = in_bias ? __ldg(in_bias + ch) : 0.f;
+  return k;
+}
+
+// P[0..3] = P(t0-2), P(t0-1), P(t0), P(t0+1) with P(t) = p[t] + ib inside [0,L) and 0 outside.
+__device__ __forceinline__ void load_window(const float* __restrict__ row, int t0, int L, bool vec, float ib,
+                                            float (&P)[4]) {
+  if (vec) {   // L even, row base 8-byte aligned, t0 even, t0 < L  =>  t0+1 < L
+    float2 a = make_float2(0.f, 0.f);
+    if (t0 >= 2) { a = *reinterpret_cast<const float2*>(row + t0 - 2); a.x += ib; a.y += ib; }
+    float2 b = *reinterpret_cast<const float2*>(row + t0);
+    P[0] = a.x; P[1] = a.y; P[2] = b.x + ib; P[3] = b.y + ib;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int t = t0 - 2 + j;
+      P[j] = (t >= 0 && t < L) ? row[t] + ib : 0.f;
+    }
+  }
+}
+
+// short filter output at t0 and t0+1 (zero for positions >= L)
+__device__ __forceinline__ float2 conv_pair(const float* __restrict__ row, int t0, int L, bool vec, const Taps& k) {
+  float P[4];
+  load_window(row, t0, L, vec, k.ib, P);
+  float2 r;
+  r.x = fmaf(k.w0, P[0], fmaf(k.w1, P[1], fmaf(k.w2, P[2], k.b)));
+  r.y = (t0 + 1 < L) ? fmaf(k.w0, P[1], fmaf(k.w1, P[2], fmaf(k.w2, P[3], k.b))) : 0.f;
+  return r;
+}
+
+__device__ __forceinline__ float2 load_pair(const float* __restrict__ row, int t0, int L, bool vec) {
+  if (vec) return *reinterpret_cast<const float2*>(row + t0);
+  return make_float2(row[t0], (t0 + 1 < L) ? row[t0 + 1] : 0.f);
+}
+__device__ __forceinline__ void store_pair(float* __restrict__ row, int t0, int L, bool vec, float2 v) {
+  if (vec) { *reinterpret_cast<float2*>(row + t0) = v; return; }
+  row[t0] = v.x;
+  if (t0 + 1 < L) row[t0 + 1] = v.y;
+}
+
+// ------------------------------------------------------------------------------------------------
+// argument blocks
+// ------------------------------------------------------------------------------------------------
+enum ColMode { COL_FILTER = 0, COL_GATE = 1, COL_DC = 2, COL_PLAIN = 3 };
+enum InvMode { INV_CONV_FWD = 0, INV_BWD_DG = 1, INV_DK = 2, INV_PLAIN_FWD = 3, INV_PLAIN_BWD = 4 };
+enum RowMode { ROW_FILTER = 0, ROW_CONV_FWD = 1, ROW_CONV_BWD = 2 };
+
+// Rows of one launch are numbered r = ci*B + b (all batches of a channel adjacent), channel c = c0 + ci.
+struct PassArgs {
+  int L;            // samples per row
+  int logM1;        // M = 2^logM1 * 1024
+  int B;            // batch
+  int D;            // channels (d_model, or H for the plain fftconv API)
+  int c0;           // first channel of this launch
+  float scale;      // 1/(4M), applied by col_inv
+  int vec;          // 1: L even and every row base 8-byte aligned -> float2 accesses
+  Twiddles T;
+  float2* A;        // scratch rows [r][k1][m2]
+  float2* A2;       // second scratch (bwd: rows of g)
+  float2* A3;       // third scratch (bwd: per-channel dK' rows [ci][k1][m2])
+  const float2* kspec;   // filter spectrum [c][k1][k2]
+  float2* kspec_out;     // ROW_FILTER output
+  // tensors (see include/hyena_b200.h for layouts)
+  const float* src;      // COL_FILTER: k (D,L); COL_PLAIN / INV_PLAIN_*: u (B,H,L); COL_DC & INV_BWD_DG: dy_pre (B,D,L)
+  const float* src2;     // INV_PLAIN_BWD: dout (B,H,L); INV_BWD_DG: c_saved (B,D,L)
+  const float* p;        // (B,3D,L) in_proj output (bias not yet added)
+  const float* in_bias;  // (3D) or null
+  const float* sw;       // (3D,3)
+  const float* sb;       // (3D)
+  const float* fbias;    // (D) filter bias / D vector of the plain API
+  float* out;            // INV_CONV_FWD: y_pre (B,D,L); INV_DK: dk (D,L); INV_PLAIN_*: out/du (B,H,L)
+  float* out2;           // INV_CONV_FWD: c_save (B,D,L) or null; INV_BWD_DG: dconv (B,3D,L)
+  float* red;            // INV_BWD_DG: dfbias (D); INV_PLAIN_BWD: dD (H)   (atomicAdd)
+};
+
+__device__ __forceinline__ size_t row_off(int b, int ch, int nch, int L) { return ((size_t)b * nch + ch) * (size_t)L; }
+
+// ------------------------------------------------------------------------------------------------
+// column-pass geometry
+// ------------------------------------------------------------------------------------------------
+template <int LOGM1>
+struct ColGeo {
+  static constexpr int M1 = 1 << LOGM1;
+  static constexpr bool TWO = LOGM1 >= 5;                       // thread-group FFT (>= 32 points)
+  static constexpr int R2 = TWO ? M1 / 32 : 1;
+  static constexpr int G = TWO ? 1 : 32 / M1;                   // columns per thread when M1 < 32
+  static constexpr int THREADS = TWO ? 256 : (32 * M1 < 256 ? 32 * M1 : 256);
+  static constexpr int C = TWO ? 256 / R2 : THREADS * G;        // columns per CTA
+  static constexpr int CTAS = kM2 / C;                          // CTAs per row
+  static constexpr int PAD = C >= 16 ? 1 : 16 / C;
+  static constexpr int PITCH = TWO ? Geo<TWO ? LOGM1 : 5>::ex_elems() + PAD : 0;   // exchange elems per column
+  static constexpr size_t SMEM = (R2 > 1) ? (size_t)C * PITCH * sizeof(float2) : 0;
+};
+
+struct CtaSync { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
+struct WarpSync { __device__ __forceinline__ void operator()() const { __syncwarp(); } };
+
+// input sample pair (x[t0], x[t0+1]) of row (b, c) for the forward column pass
+template <int MODE>
+__device__ __forceinline__ float2 col_input(const PassArgs& a, int b, int c, int t0, bool vec,
+                                            const Taps& ka, const Taps& kb) {
+  if constexpr (MODE == COL_FILTER) {
+    return load_pair(a.src + (size_t)c * a.L, t0, a.L, vec);
+  } else if constexpr (MODE == COL_PLAIN) {
+    return load_pair(a.src + row_off(b, c, a.D, a.L), t0, a.L, vec);
+  } else if constexpr (MODE == COL_GATE) {      // g = short(v) * short(x1)        hyena.py:420
+    float2 x1 = conv_pair(a.p + row_off(b, a.D + c, 3 * a.D, a.L), t0, a.L, vec, ka);
+    float2 v = conv_pair(a.p + row_off(b, 2 * a.D + c, 3 * a.D, a.L), t0, a.L, vec, kb);
+    return make_float2(x1.x * v.x, x1.y * v.y);
+  } else {                                       // COL_DC: dc = dy_pre * short(x0)
+    float2 x0 = conv_pair(a.p + row_off(b, c, 3 * a.D, a.L), t0, a.L, vec, ka);
+    float2 dy = load_pair(a.src + row_off(b, c, a.D, a.L), t0, a.L, vec);
+    return make_float2(x0.x * dy.x, x0.y * dy.y);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 1: forward column FFT with the input side fused in
+// grid (CTAS, rows); block ColGeo::THREADS
+// ------------------------------------------------------------------------------------------------
+template <int LOGM1, int MODE>
+__global__ void __launch_bounds__(ColGeo<LOGM1>::THREADS, ColGeo<LOGM1>::TWO ? 2 : 1)
+col_fwd_kernel(const PassArgs a) {
+  using CG = ColGeo<LOGM1>;
+  constexpr int M1 = CG::M1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* smem = reinterpret_cast<float2*>(smem_raw);
+
+  const int r = blockIdx.y;
+  const int ci = r / a.B, b = r - ci * a.B, c = a.c0 + ci;
+  const int colbase = blockIdx.x * CG::C;
+  const int L = a.L;
+  const bool vec = a.vec != 0;
+  const int logM = LOGM1 + kLogM2;
+  float2* Arow = a.A + (size_t)r * ((size_t)M1 * kM2);
+
+  Taps ka{}, kb{};
+  if constexpr (MODE == COL_GATE) {
+    ka = load_taps(a.sw, a.sb, a.in_bias, a.D + c);
+    kb = load_taps(a.sw, a.sb, a.in_bias, 2 * a.D + c);
+  } else if constexpr (MODE == COL_DC) {
+    ka = load_taps(a.sw, a.sb, a.in_bias, c);
+  }
+
+  float2 v[32];
+  if constexpr (CG::TWO) {
+    const int col = threadIdx.x % CG::C, q = threadIdx.x / CG::C;
+    const int m2 = colbase + col;
+    // slots n1 >= 16 (m1 >= M1/2) are the zero padding: never loaded
+    static_for<0, 16>([&](auto n_) {
+      constexpr int n1 = decltype(n_)::value;
+      const int m1 = CG::R2 * n1 + q;
+      const int t0 = 2 * (m1 * kM2 + m2);
+      v[n1] = (t0 < L) ? col_input<MODE>(a, b, c, t0, vec, ka, kb) : make_float2(0.f, 0.f);
+    });
+    static_for<16, 32>([&](auto n_) { v[decltype(n_)::value] = make_float2(0.f, 0.f); });
+    block_fft<CG::TWO ? LOGM1 : 5, false, true>(v, smem + col * CG::PITCH, q, a.T.tw1024, CtaSync{});
+    // 4-step twiddle W_M^{m2*k1}, k1 = R2*s + q : geometric in s
+    const int sh = 20 - logM;
+    const uint32_t Mmask = (1u << logM) - 1u;
+    const uint32_t eb = ((uint32_t)m2 * (uint32_t)q) & Mmask;
+    const uint32_t es = ((uint32_t)m2 * (uint32_t)CG::R2) & Mmask;
+    float2 base = root20(a.T, eb << sh);
+    float2 s1 = root20(a.T, (es & Mmask) << sh);
+    float2 s2 = root20(a.T, ((2u * es) & Mmask) << sh);
+    float2 s4 = root20(a.T, ((4u * es) & Mmask) << sh);
+    float2 s8 = root20(a.T, ((8u * es) & Mmask) << sh);
+    float2 s16 = root20(a.T, ((16u * es) & Mmask) << sh);
+    mul_geometric<false>(v, base, s1, s2, s4, s8, s16, SlotIdx<CG::TWO ? LOGM1 : 5>{});
+    static_for<0, 32>([&](auto s_) {
+      constexpr int s = decltype(s_)::value;
+      const int k1 = CG::R2 * s + q;
+      Arow[(size_t)k1 * kM2 + m2] = v[Geo<CG::TWO ? LOGM1 : 5>::slot(s)];
+    });
+  } else {
+    // M1 < 32: a thread owns G whole columns; column gi lives in v[gi*M1 .. gi*M1+M1)
+    static_for<0, CG::G>([&](auto g_) {
+      constexpr int gi = decltype(g_)::value;
+      const int m2 = colbase + threadIdx.x + CG::THREADS * gi;
+      static_for<0, M1>([&](auto m_) {
+        constexpr int m1 = decltype(m_)::value;
+        const int t0 = 2 * (m1 * kM2 + m2);
+        v[gi * M1 + m1] = (t0 < L) ? col_input<MODE>(a, b, c, t0, vec, ka, kb) : make_float2(0.f, 0.f);
+      });
+      dif<M1, gi * M1, false, 32>(v);
+      static_for<0, M1>([&](auto k_) {
+        constexpr int k1 = decltype(k_)::value;
+        float2 x = v[gi * M1 + brev(k1, LOGM1)];
+        if constexpr (k1 > 0) {
+          const uint32_t e = ((uint32_t)m2 * (uint32_t)k1) & ((1u << logM) - 1u);
+          x = cmul(x, root20(a.T, e << (20 - logM)));
+        }
+        Arow[(size_t)k1 * kM2 + m2] = x;
+      });
+    });
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 3: inverse column FFT with the output side fused in
+// ------------------------------------------------------------------------------------------------
+struct InvCtx {
+  Taps k0, k1, k2;     // taps of x0, x1, v channels
+  float fb;            // filter bias of this channel
+  float red;           // per-thread partial of the reduction this mode produces
+};
+
+// y = (y[t0], y[t0+1]) already scaled
+template <int MODE>
+__device__ __forceinline__ void inv_output(const PassArgs& a, InvCtx& cx, int b, int c, int t0, bool vec, float2 y) {
+  const int L = a.L, D = a.D;
+  if constexpr (MODE == INV_DK) {
+    store_pair(a.out + (size_t)c * L, t0, L, vec, y);
+  } else if constexpr (MODE == INV_PLAIN_FWD) {       // out = y + u * D      hyena.py:82
+    float2 u = load_pair(a.src + row_off(b, c, D, L), t0, L, vec);
+    store_pair(a.out + row_off(b, c, D, L), t0, L, vec, make_float2(fmaf(u.x, cx.fb, y.x), fmaf(u.y, cx.fb, y.y)));
+  } else if constexpr (MODE == INV_PLAIN_BWD) {       // du = corr + dout * D ; dD += dout * u
+    float2 d = load_pair(a.src2 + row_off(b, c, D, L), t0, L, vec);
+    float2 u = load_pair(a.src + row_off(b, c, D, L), t0, L, vec);
+    cx.red = fmaf(d.x, u.x, fmaf(d.y, u.y, cx.red));
+    store_pair(a.out + row_off(b, c, D, L), t0, L, vec, make_float2(fmaf(d.x, cx.fb, y.x), fmaf(d.y, cx.fb, y.y)));
+  } else if constexpr (MODE == INV_CONV_FWD) {        // c = y + bias*g ; y_pre = c * x0     hyena.py:82, :432
+    float2 x0 = conv_pair(a.p + row_off(b, c, 3 * D, L), t0, L, vec, cx.k0);
+    float2 x1 = conv_pair(a.p + row_off(b, D + c, 3 * D, L), t0, L, vec, cx.k1);
+    float2 vv = conv_pair(a.p + row_off(b, 2 * D + c, 3 * D, L), t0, L, vec, cx.k2);
+    float2 cc = make_float2(fmaf(x1.x * vv.x, cx.fb, y.x), fmaf(x1.y * vv.y, cx.fb, y.y));
+    if (a.out2) store_pair(a.out2 + row_off(b, c, D, L), t0, L, vec, cc);
+    store_pair(a.out + row_off(b, c, D, L), t0, L, vec, make_float2(cc.x * x0.x, cc.y * x0.y));
+  } else {                                            // INV_BWD_DG
+    float2 x0 = conv_pair(a.p + row_off(b, c, 3 * D, L), t0, L, vec, cx.k0);
+    float2 x1 = conv_pair(a.p + row_off(b, D + c, 3 * D, L), t0, L, vec, cx.k1);
+    float2 vv = conv_pair(a.p + row_off(b, 2 * D + c, 3 * D, L), t0, L, vec, cx.k2);
+    float2 dy = load_pair(a.src + row_off(b, c, D, L), t0, L, vec);
+    float2 cs = load_pair(a.src2 + row_off(b, c, D, L), t0, L, vec);
+    float2 dc = make_float2(dy.x * x0.x, dy.y * x0.y);
+    float2 dg = make_float2(fmaf(dc.x, cx.fb, y.x), fmaf(dc.y, cx.fb, y.y));     // + bias * dc
+    cx.red = fmaf(dc.x, x1.x * vv.x, fmaf(dc.y, x1.y * vv.y, cx.red));           // dbias += dc * g
+    store_pair(a.out2 + row_off(b, c, 3 * D, L), t0, L, vec, make_float2(dy.x * cs.x, dy.y * cs.y));           // d x0c
+    store_pair(a.out2 + row_off(b, D + c, 3 * D, L), t0, L, vec, make_float2(dg.x * vv.x, dg.y * vv.y));       // d x1c
+    store_pair(a.out2 + row_off(b, 2 * D + c, 3 * D, L), t0, L, vec, make_float2(dg.x * x1.x, dg.y * x1.y));   // d vc
+  }
+}
+
+template <int LOGM1, int MODE>
+__global__ void __launch_bounds__(ColGeo<LOGM1>::THREADS, ColGeo<LOGM1>::TWO ? 2 : 1)
+col_inv_kernel(const PassArgs a) {
+  using CG = ColGeo<LOGM1>;
+  constexpr int M1 = CG::M1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* smem = reinterpret_cast<float2*>(smem_raw);
+  __shared__ float red_smem[8];
+
+  const int r = blockIdx.y;
+  const int ci = r / a.B, b = r - ci * a.B, c = a.c0 + ci;
+  const int colbase = blockIdx.x * CG::C;
+  const int L = a.L;
+  const bool vec = a.vec != 0;
+  const float2* Arow = (MODE == INV_DK ? a.A3 : a.A) + (size_t)r * ((size_t)M1 * kM2);
+
+  InvCtx cx{};
+  cx.red = 0.f;
+  if constexpr (MODE == INV_CONV_FWD || MODE == INV_BWD_DG) {
+    cx.k0 = load_taps(a.sw, a.sb, a.in_bias, c);
+    cx.k1 = load_taps(a.sw, a.sb, a.in_bias, a.D + c);
+    cx.k2 = load_taps(a.sw, a.sb, a.in_bias, 2 * a.D + c);
+  }
+  if constexpr (MODE != INV_DK) cx.fb = __ldg(a.fbias + c);
+
+  float2 v[32];
+  if constexpr (CG::TWO) {
+    const int col = threadIdx.x % CG::C, q = threadIdx.x / CG::C;
+    const int m2 = colbase + col;
+    static_for<0, 32>([&](auto n_) {
+      constexpr int n1 = decltype(n_)::value;
+      v[n1] = Arow[(size_t)(CG::R2 * n1 + q) * kM2 + m2];
+    });
+    block_fft<CG::TWO ? LOGM1 : 5, true, false>(v, smem + col * CG::PITCH, q, a.T.tw1024, CtaSync{});
+    // only m1 < M1/2 (slots s < 16) can hold samples t < L
+    static_for<0, 16>([&](auto s_) {
+      constexpr int s = decltype(s_)::value;
+      const int m1 = CG::R2 * s + q;
+      const int t0 = 2 * (m1 * kM2 + m2);
+      if (t0 < L) {
+        float2 y = v[Geo<CG::TWO ? LOGM1 : 5>::slot(s)];
+        inv_output<MODE>(a, cx, b, c, t0, vec, make_float2(y.x * a.scale, y.y * a.scale));
+      }
+    });
+  } else {
+    static_for<0, CG::G>([&](auto g_) {
+      constexpr int gi = decltype(g_)::value;
+      const int m2 = colbase + threadIdx.x + CG::THREADS * gi;
+      static_for<0, M1>([&](auto k_) {
+        constexpr int k1 = decltype(k_)::value;
+        v[gi * M1 + k1] = Arow[(size_t)k1 * kM2 + m2];
+      });
+      dif<M1, gi * M1, true, 32>(v);
+      static_for<0, (M1 >= 2 ? M1 / 2 : 1)>([&](auto m_) {
+        constexpr int m1 = decltype(m_)::value;
+        const int t0 = 2 * (m1 * kM2 + m2);
+        if (t0 < L) {
+          float2 y = v[gi * M1 + brev(m1, LOGM1)];
+          inv_output<MODE>(a, cx, b, c, t0, vec, make_float2(y.x * a.scale, y.y * a.scale));
+        }
+      });
+    });
+  }
+
+  if constexpr (MODE == INV_BWD_DG || MODE == INV_PLAIN_BWD) {
+    float s = cx.red;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red_smem[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < (CG::THREADS + 31) / 32; ++w) tot += red_smem[w];
+      atomicAdd(a.red + c, tot);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 2: row FFTs + pointwise spectrum product + inverse row FFTs
+// One warp per k1 row; warps 2i / 2i+1 of a CTA hold the two rows of a (k, M-k) pair.
+// grid (max(1, M1/8), channel-rows); block 32 * min(8, M1)
+// ------------------------------------------------------------------------------------------------
+constexpr int kRowEx = 32 * 33;                       // exchange elems of one 1024-point transform
+constexpr int kRowPitch = kRowEx;
+
+struct RowIds {
+  int k1;        // this warp's row
+  int pk1;       // row holding the partner bins
+  int pwarp;     // warp of this CTA that holds row pk1
+  int nz;        // 1 if k1 != 0 (partner column is M2-1-k2 instead of (M2-k2)%M2)
+};
+
+__device__ __forceinline__ RowIds row_ids(int M1, int cta, int warp) {
+  RowIds id;
+  if (M1 == 1) { id.k1 = 0; id.pk1 = 0; id.pwarp = 0; id.nz = 0; return id; }
+  const int pair = cta * 4 + (warp >> 1);        // pair 0 = rows (0, M1/2), both self-paired
+  const int second = warp & 1;
+  if (pair == 0) {
+    id.k1 = second ? M1 / 2 : 0;
+    id.pk1 = id.k1; id.pwarp = warp;
+  } else {
+    id.k1 = second ? M1 - pair : pair;
+    id.pk1 = M1 - id.k1; id.pwarp = warp ^ 1;
+  }
+  id.nz = id.k1 != 0;
+  return id;
+}
+
+// 1024-point forward FFT of row `src` by one warp; natural bin k2 = 32*s + lane left in dst[k2] (shared).
+__device__ __forceinline__ void row_fft_to_smem(const float2* __restrict__ src, float2* ex, float2* dst, int lane,
+                                                const float2* tw1024) {
+  float2 v[32];
+  static_for<0, 32>([&](auto n_) {
+    constexpr int n1 = decltype(n_)::value;
+    v[n1] = src[32 * n1 + lane];
+  });
+  block_fft<10, false, false>(v, ex, lane, tw1024, WarpSync{});
+  static_for<0, 32>([&](auto s_) {
+    constexpr int s = decltype(s_)::value;
+    dst[32 * s + lane] = v[Geo<10>::slot(s)];
+  });
+}
+
+// inverse 1024-point FFT of v (natural slots), conj 4-step twiddle, store to dst[m2 = 32*s + lane]
+__device__ __forceinline__ void row_ifft_store(float2 (&v)[32], float2* ex, float2* __restrict__ dst, int lane, int k1,
+                                               int logM, const Twiddles& T) {
+  block_fft<10, true, false>(v, ex, lane, T.tw1024, WarpSync{});
+  const int sh = 20 - logM;
+  const uint32_t Mmask = (1u << logM) - 1u;
+  const uint32_t eb = ((uint32_t)k1 * (uint32_t)lane) & Mmask;
+  const uint32_t es = ((uint32_t)k1 * 32u) & Mmask;
+  float2 base = root20(T, eb << sh);
+  float2 s1 = root20(T, (es & Mmask) << sh);
+  float2 s2 = root20(T, ((2u * es) & Mmask) << sh);
+  float2 s4 = root20(T, ((4u * es) & Mmask) << sh);
+  float2 s8 = root20(T, ((8u * es) & Mmask) << sh);
+  float2 s16 = root20(T, ((16u * es) & Mmask) << sh);
+  mul_geometric<true>(v, base, s1, s2, s4, s8, s16, SlotIdx<10>{});
+  static_for<0, 32>([&](auto s_) {
+    constexpr int s = decltype(s_)::value;
+    dst[32 * s + lane] = v[Geo<10>::slot(s)];
+  });
+}
+
+// E2 = Z + conj(P), O2 = -i (Z - conj(P))    (P already conjugated by the caller)
+__device__ __forceinline__ void even_odd(float2 z, float2 pc, float2& e, float2& o) {
+  e = cadd(z, pc);
+  o = cmul_negi(csub(z, pc));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256, MODE == ROW_CONV_BWD ? 1 : 2)
+row_pass_kernel(const PassArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* smem = reinterpret_cast<float2*>(smem_raw);
+  const int M1 = 1 << a.logM1;
+  const int logM = a.logM1 + kLogM2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+  const RowIds id = row_ids(M1, blockIdx.x, warp);
+  const size_t rowElems = (size_t)M1 * kM2;
+
+  // shared memory carve-up: per-warp exchange, then per-warp natural-order spectrum buffers
+  float2* ex = smem + warp * kRowPitch;
+  float2* zbuf = smem + nwarps * kRowPitch;            // [warp][1024]   (ROW_CONV_*)
+  float2* gbuf = zbuf + nwarps * kM2;                  // [warp][1024]   (ROW_CONV_BWD)
+
+  if constexpr (MODE == ROW_FILTER) {
+    const int c = a.c0 + blockIdx.y;
+    const float2* src = a.A + (size_t)blockIdx.y * rowElems + (size_t)id.k1 * kM2;
+    float2* dst = a.kspec_out + (size_t)c * rowElems + (size_t)id.k1 * kM2;
+    float2 v[32];
+    static_for<0, 32>([&](auto n_) { constexpr int n1 = decltype(n_)::value; v[n1] = src[32 * n1 + lane]; });
+    block_fft<10, false, false>(v, ex, lane, a.T.tw1024, WarpSync{});
+    static_for<0, 32>([&](auto s_) {
+      constexpr int s = decltype(s_)::value;
+      dst[32 * s + lane] = v[Geo<10>::slot(s)];
+    });
+    return;
+  } else {
+    // W_M^k for k = k1 + M1*(32 s + lane) = base * W_32^s,  base = W_M^{k1} * W_1024^{lane}
+    const float2 wbase = cmul(root20(a.T, (uint32_t)id.k1 << (20 - logM)), __ldg(a.T.tw1024 + lane));
+
+    if constexpr (MODE == ROW_CONV_FWD) {
+      const int r = blockIdx.y;
+      const int ci = r / a.B, c = a.c0 + ci;
+      float2* Arow = a.A + (size_t)r * rowElems + (size_t)id.k1 * kM2;
+      const float2* Krow = a.kspec + (size_t)c * rowElems + (size_t)id.k1 * kM2;
+      const float2* Kprow = a.kspec + (size_t)c * rowElems + (size_t)id.pk1 * kM2;
+      row_fft_to_smem(Arow, ex, zbuf + warp * kM2, lane, a.T.tw1024);
+      __syncthreads();
+      const float2* zme = zbuf + warp * kM2;
+      const float2* zpa = zbuf + id.pwarp * kM2;
+      float2 v[32];
+      static_for<0, 32>([&](auto s_) {
+        constexpr int s = decltype(s_)::value;
+        const int k2 = 32 * s + lane;
+        const int pc = (kM2 - k2 - id.nz) & (kM2 - 1);
+        float2 E, O, He, Ho;
+        even_odd(zme[k2], cconj(zpa[pc]), E, O);
+        even_odd(__ldg(Krow + k2), cconj(__ldg(Kprow + pc)), He, Ho);
+        const float2 W = mul_w32<s, false>(wbase);
+        float2 Ye = cadd(cmul(E, He), cmul(W, cmul(O, Ho)));
+        float2 Yo = cadd(cmul(E, Ho), cmul(O, He));
+        v[s] = cadd(Ye, cmul_i(Yo));
+      });
+      row_ifft_store(v, ex, Arow, lane, id.k1, logM, a.T);
+    } else {   // ROW_CONV_BWD: loop over the batch, accumulate dK' in registers
+      const int ci = blockIdx.y, c = a.c0 + ci;
+      const float2* Krow = a.kspec + (size_t)c * rowElems + (size_t)id.k1 * kM2;
+      const float2* Kprow = a.kspec + (size_t)c * rowElems + (size_t)id.pk1 * kM2;
+      float2 acc[32];
+      static_for<0, 32>([&](auto s_) { acc[decltype(s_)::value] = make_float2(0.f, 0.f); });
+      for (int b = 0; b < a.B; ++b) {
+        const size_t r = (size_t)ci * a.B + b;
+        float2* Drow = a.A + r * rowElems + (size_t)id.k1 * kM2;
+        const float2* Grow = a.A2 + r * rowElems + (size_t)id.k1 * kM2;
+        if (b > 0) __syncthreads();                   // previous iteration's readers of zbuf/gbuf are done
+        row_fft_to_smem(Drow, ex, zbuf + warp * kM2, lane, a.T.tw1024);
+        __syncwarp();
+        row_fft_to_smem(Grow, ex, gbuf + warp * kM2, lane, a.T.tw1024);
+        __syncthreads();
+        const float2* zme = zbuf + warp * kM2;
+        const float2* zpa = zbuf + id.pwarp * kM2;
+        const float2* gme = gbuf + warp * kM2;
+        const float2* gpa = gbuf + id.pwarp * kM2;
+        float2 v[32];
+        static_for<0, 32>([&](auto s_) {
+          constexpr int s = decltype(s_)::value;
+          const int k2 = 32 * s + lane;
+          const int pc = (kM2 - k2 - id.nz) & (kM2 - 1);
+          float2 E, O, He, Ho, Ge, Go;
+          even_odd(zme[k2], cconj(zpa[pc]), E, O);
+          even_odd(__ldg(Krow + k2), cconj(__ldg(Kprow + pc)), He, Ho);
+          even_odd(gme[k2], cconj(gpa[pc]), Ge, Go);
+          const float2 W = mul_w32<s, false>(wbase);
+          const float2 WE = cmulc(E, W);                                  // conj(W) * E
+          // dg spectrum: corr(dc, k)
+          float2 Ye = cadd(cmulc(E, He), cmulc(O, Ho));
+          float2 Yo = cadd(cmulc(WE, Ho), cmulc(O, He));
+          v[s] = cadd(Ye, cmul_i(Yo));
+          // dk spectrum: corr(dc, g), summed over the batch
+          float2 Ke = cadd(cmulc(E, Ge), cmulc(O, Go));
+          float2 Ko = cadd(cmulc(WE, Go), cmulc(O, Ge));
+          acc[s] = cadd(acc[s], cadd(Ke, cmul_i(Ko)));
+        });
+        row_ifft_store(v, ex, Drow, lane, id.k1, logM, a.T);
+      }
+      float2* Krow_out = a.A3 + (size_t)ci * rowElems + (size_t)id.k1 * kM2;
+      __syncwarp();                                   // the exchange area is reused right away
+      row_ifft_store(acc, ex, Krow_out, lane, id.k1, logM, a.T);
+    }
+  }
+}
+
+}  // namespace hy

@@ -1,0 +1,43 @@
+#include "launch.h"
+namespace hy {
+
+template <int LOGM1, int MODE>
+static cudaError_t go(const PassArgs& a, int rows, cudaStream_t s) {
+  using CG = ColGeo<LOGM1>;
+  auto kern = col_fwd_kernel<LOGM1, MODE>;
+  cudaError_t e = set_smem(kern, CG::SMEM);
+  if (e != cudaSuccess) return e;
+  kern<<<dim3(CG::CTAS, rows), CG::THREADS, CG::SMEM, s>>>(a);
+  count_launch();
+  return cudaGetLastError();
+}
+
+template <int MODE>
+static cudaError_t by_size(const PassArgs& a, int rows, cudaStream_t s) {
+  switch (a.logM1) {
+    case 0: return go<0, MODE>(a, rows, s);
+    case 1: return go<1, MODE>(a, rows, s);
+    case 2: return go<2, MODE>(a, rows, s);
+    case 3: return go<3, MODE>(a, rows, s);
+    case 4: return go<4, MODE>(a, rows, s);
+    case 5: return go<5, MODE>(a, rows, s);
+    case 6: return go<6, MODE>(a, rows, s);
+    case 7: return go<7, MODE>(a, rows, s);
+    case 8: return go<8, MODE>(a, rows, s);
+    case 9: return go<9, MODE>(a, rows, s);
+    case 10: return go<10, MODE>(a, rows, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_col_fwd(int mode, const PassArgs& a, int rows, cudaStream_t s) {
+  switch (mode) {
+    case COL_FILTER: return by_size<COL_FILTER>(a, rows, s);
+    case COL_GATE: return by_size<COL_GATE>(a, rows, s);
+    case COL_DC: return by_size<COL_DC>(a, rows, s);
+    case COL_PLAIN: return by_size<COL_PLAIN>(a, rows, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace hy

@@ -1,0 +1,24 @@
+// Host-side launch entry points implemented in the k_*.cu translation units.
+#pragma once
+#include "fft_passes.cuh"
+#include "filter_mlp.cuh"
+#include "short_conv.cuh"
+
+namespace hy {
+
+void count_launch();                       // api.cu
+cudaError_t launch_col_fwd(int mode, const PassArgs& a, int rows, cudaStream_t s);
+cudaError_t launch_col_inv(int mode, const PassArgs& a, int rows, cudaStream_t s);
+cudaError_t launch_row_pass(int mode, const PassArgs& a, int rows, cudaStream_t s);
+cudaError_t launch_filter_fwd(const FilterParams& P, float* kout, cudaStream_t s);
+cudaError_t launch_filter_bwd(const FilterParams& P, const float* dk, const FilterGrads& G, cudaStream_t s);
+cudaError_t launch_short_bwd(const ShortBwdArgs& a, int B, cudaStream_t s);
+cudaError_t launch_twiddle_init(float2* tw1024, float2* twlo, cudaStream_t s);
+
+template <class K>
+inline cudaError_t set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  return cudaSuccess;
+}
+
+}  // namespace hy

@@ -1,0 +1,238 @@
+"""Drop-in HyenaOperator / HyenaFilter backed by the sm_100a library.
+
+Mirrors the public surface of /root/reference/src/models/sequence/hyena.py (same class names,
+constructor keywords, state_dict keys and shapes, ``_optim`` attributes, ``filter(L)`` /
+``forward`` semantics) for the configuration the HyenaDNA models use -- order=2, num_heads=1,
+num_blocks=1, inner_factor=1, activation="id", dropout=0 -- and raises a clear error for options
+outside that scope instead of silently diverging.  There is no CPU fallback.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import HyenaB200Error
+
+
+class OptimModule(nn.Module):
+    """register(name, tensor, lr): lr == 0 -> buffer, else Parameter carrying ``_optim`` hyper-parameters
+    (src/utils/train.py:142-155)."""
+
+    def register(self, name, tensor, lr=None, wd=0.0):
+        if lr == 0.0:
+            self.register_buffer(name, tensor)
+        else:
+            self.register_parameter(name, nn.Parameter(tensor))
+            optim = {}
+            if lr is not None:
+                optim["lr"] = lr
+            if wd is not None:
+                optim["weight_decay"] = wd
+            setattr(getattr(self, name), "_optim", optim)
+
+
+class Sin(nn.Module):
+    """sin(freq * x) with one trainable frequency per feature (hyena.py:96-106).  Kept as a module so
+    the state_dict carries ``implicit_filter.{1,3,5}.freq``; evaluated inside the fused filter kernel."""
+
+    def __init__(self, dim, w=10, train_freq=True):
+        super().__init__()
+        self.freq = nn.Parameter(w * torch.ones(1, dim)) if train_freq else w * torch.ones(1, dim)
+
+    def forward(self, x):
+        return torch.sin(self.freq * x)
+
+
+class PositionalEmbedding(OptimModule):
+    """z (1, L, emb_dim) = [t, cos(f w), -sin(f w)], t (1, L, 1) = linspace(0, 1, L)  (hyena.py:109-131)."""
+
+    def __init__(self, emb_dim, seq_len, lr_pos_emb=1e-5, **kwargs):
+        super().__init__()
+        self.seq_len = seq_len
+        t = torch.linspace(0, 1, seq_len)[None, :, None]
+        bands = (emb_dim - 1) // 2
+        pos = torch.linspace(0, seq_len - 1, seq_len)[None, :, None]
+        w = 2 * math.pi * pos / seq_len
+        f = torch.linspace(1e-4, bands - 1, bands)[None, None]
+        zc = torch.exp(-1j * f * w)
+        self.register("z", torch.cat([t, zc.real, zc.imag], dim=-1), lr=lr_pos_emb)
+        self.register("t", t, lr=0.0)
+
+    def forward(self, L):
+        return self.z[:, :L], self.t[:, :L]
+
+
+class ExponentialModulation(OptimModule):
+    """h * (exp(-t |deltas|) + shift)  (hyena.py:134-155); evaluated inside the fused filter kernel."""
+
+    def __init__(self, d_model, fast_decay_pct=0.3, slow_decay_pct=1.5, target=1e-2, modulation_lr=0.0,
+                 shift=0.0, **kwargs):
+        super().__init__()
+        self.shift = shift
+        max_decay = math.log(target) / fast_decay_pct
+        min_decay = math.log(target) / slow_decay_pct
+        self.register("deltas", torch.linspace(min_decay, max_decay, d_model)[None, None], lr=modulation_lr)
+
+    def forward(self, t, x):
+        return x * (torch.exp(-t * self.deltas.abs()) + self.shift)
+
+
+class HyenaFilter(OptimModule):
+    """Implicit long filter (hyena.py:158-267).  ``filter(L)`` -> (1, L, D); ``forward(x, L, k, bias)`` ->
+    causal FFT convolution of x (..., D, L) with k plus the bias skip term."""
+
+    def __init__(self, d_model, emb_dim=3, order=16, fused_fft_conv=False, seq_len=1024, lr=1e-3, lr_pos_emb=1e-5,
+                 dropout=0.0, w=1, wd=0, bias=True, num_inner_mlps=2, linear_mixer=False, modulate=True,
+                 normalized=False, bidirectional=False, **kwargs):
+        super().__init__()
+        if linear_mixer or normalized or bidirectional or num_inner_mlps != 2 or dropout != 0.0:
+            raise HyenaB200Error("HyenaFilter: linear_mixer / normalized / bidirectional / num_inner_mlps != 2 / "
+                                 "dropout are outside the sm_100a hot path (no fallback)")
+        if order != 64:
+            raise HyenaB200Error(f"HyenaFilter: filter order {order} not supported by the fused kernel (64 only)")
+        assert emb_dim % 2 != 0 and emb_dim >= 3, "emb_dim must be odd and greater or equal to 3 (time, sine and cosine)"
+        self.d_model, self.emb_dim, self.seq_len, self.modulate = d_model, emb_dim, seq_len, modulate
+        self.use_bias = bias
+        self.fused_fft_conv = fused_fft_conv      # accepted for config compatibility; the fused path is always on
+        self.bias = nn.Parameter(torch.randn(d_model))
+        self.dropout = nn.Dropout(dropout)
+        self.bidirectional = bidirectional
+        self.normalized = normalized
+
+        act = Sin(dim=order, w=w)
+        self.pos_emb = PositionalEmbedding(emb_dim, seq_len, lr_pos_emb)
+        self.implicit_filter = nn.Sequential(nn.Linear(emb_dim, order), act)
+        for _ in range(num_inner_mlps):
+            self.implicit_filter.append(nn.Linear(order, order))
+            self.implicit_filter.append(act)
+        self.implicit_filter.append(nn.Linear(order, d_model, bias=False))
+        self.modulation = ExponentialModulation(d_model, **kwargs)
+        for c in self.implicit_filter.children():
+            for name, _ in c.state_dict().items():
+                setattr(getattr(c, name), "_optim", {"weight_decay": wd, "lr": lr})
+
+    def filter_channel_major(self, L):
+        """k (D, L): the layout the convolution kernels consume."""
+        f = self.implicit_filter
+        return ops.HyenaFilterFn.apply(self.pos_emb.z, self.pos_emb.t, f[0].weight, f[0].bias, f[2].weight, f[2].bias,
+                                       f[4].weight, f[4].bias, f[6].weight, f[1].freq, self.modulation.deltas,
+                                       float(self.modulation.shift), bool(self.modulate), int(L))
+
+    def filter(self, L, *args, **kwargs):
+        return self.filter_channel_major(L).transpose(0, 1).unsqueeze(0)
+
+    def forward(self, x, L, k=None, bias=None, *args, **kwargs):
+        from .fftconv import fftconv_func
+        if k is None:
+            k = self.filter_channel_major(L)
+        else:
+            k = k[0] if type(k) is tuple else k
+            if k.dim() == 3:
+                k = k[0].transpose(0, 1)
+        if bias is None:
+            bias = self.bias
+        bias = bias if self.use_bias else 0 * bias
+        shape = x.shape
+        y = fftconv_func(x.reshape(-1, shape[-2], shape[-1]), k, bias.reshape(-1).to(torch.float32), gelu=False)
+        return y.reshape(shape).to(dtype=x.dtype)
+
+
+class _InProj(torch.autograd.Function):
+    """p = W u^T written channel-major (B, 3D, L) straight from cuBLAS: no transpose pass
+    (replaces hyena.py:391-392).  The bias is added inside the fused kernels."""
+
+    @staticmethod
+    def forward(ctx, u, W):
+        ctx.save_for_backward(u, W)
+        B = u.shape[0]
+        return torch.bmm(W.unsqueeze(0).expand(B, -1, -1), u.transpose(1, 2))
+
+    @staticmethod
+    def backward(ctx, dp):
+        u, W = ctx.saved_tensors
+        du = torch.matmul(dp.transpose(1, 2), W) if ctx.needs_input_grad[0] else None
+        dW = torch.bmm(dp, u).sum(0) if ctx.needs_input_grad[1] else None
+        return du, dW
+
+
+class _OutProj(torch.autograd.Function):
+    """y = y_pre^T W^T + b consuming channel-major y_pre (B, D, L) (replaces hyena.py:432-440)."""
+
+    @staticmethod
+    def forward(ctx, y_pre, W, b):
+        ctx.save_for_backward(y_pre, W)
+        B = y_pre.shape[0]
+        y = torch.bmm(y_pre.transpose(1, 2), W.t().unsqueeze(0).expand(B, -1, -1))
+        if b is not None:
+            y += b
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y_pre, W = ctx.saved_tensors
+        B = dy.shape[0]
+        d_pre = torch.bmm(W.t().unsqueeze(0).expand(B, -1, -1), dy.transpose(1, 2)) if ctx.needs_input_grad[0] else None
+        dW = torch.bmm(dy.transpose(1, 2), y_pre.transpose(1, 2)).sum(0) if ctx.needs_input_grad[1] else None
+        db = dy.sum((0, 1)) if ctx.needs_input_grad[2] else None
+        return d_pre, dW, db
+
+
+class HyenaOperator(nn.Module):
+    """Hyena operator (hyena.py:270-448), order-2 hot path on sm_100a.
+
+    forward(u: (B, L, D)) -> (B, L, D) (or ``(y, None)`` when return_state).  Unknown keyword arguments
+    (layer_idx, device, dtype, ...) fall through to the filter exactly as in the reference."""
+
+    def __init__(self, d_model, l_max, order=2, filter_order=64, num_heads=1, inner_factor=1, num_blocks=1,
+                 fused_bias_fc=False, outer_mixing=False, dropout=0.0, filter_dropout=0.0, filter_cls="hyena-filter",
+                 post_order_ffn=False, jit_filter=False, short_filter_order=3, activation="id", return_state=False,
+                 **filter_args):
+        super().__init__()
+        unsupported = {"order": order != 2, "num_heads": num_heads != 1, "inner_factor": inner_factor != 1,
+                       "num_blocks": num_blocks != 1, "outer_mixing": outer_mixing, "dropout": dropout != 0.0,
+                       "filter_dropout": filter_dropout != 0.0, "post_order_ffn": post_order_ffn,
+                       "jit_filter": jit_filter, "short_filter_order": short_filter_order != 3,
+                       "activation": activation not in ("id", "identity", None),
+                       "filter_cls": filter_cls != "hyena-filter", "fused_bias_fc": fused_bias_fc}
+        bad = [k for k, v in unsupported.items() if v]
+        if bad:
+            raise HyenaB200Error(f"HyenaOperator options outside the sm_100a hot path (no fallback): {bad}")
+        self.d_model, self.l_max, self.order = d_model, l_max, order
+        self.num_heads, self.inner_factor, self.num_blocks = num_heads, inner_factor, num_blocks
+        self.block_dim, self.head_dim = l_max // num_blocks, d_model // num_heads
+        self.filter_order, self.short_filter_order = filter_order, short_filter_order
+        self.post_order_ffn, self.jit_filter, self.outer_mixing = post_order_ffn, jit_filter, outer_mixing
+        self.filter_dropout, self.return_state = filter_dropout, return_state
+        self.activation = nn.Identity()
+        self.dropout = nn.Dropout(dropout)
+        self.out_proj = nn.Linear(d_model * inner_factor, d_model)
+        self.in_proj = nn.Linear(d_model, (order + 1) * d_model)
+        total_width = d_model * inner_factor * (order + 1)
+        self.short_filter = nn.Conv1d(total_width, total_width, short_filter_order, groups=total_width,
+                                      padding=short_filter_order - 1)
+        filter_args.pop("channels", None)
+        self.filter_fn = HyenaFilter(self.head_dim * inner_factor * (order - 1), order=filter_order, seq_len=l_max,
+                                     channels=1, dropout=filter_dropout, **filter_args)
+
+    def forward(self, u, *args, **kwargs):
+        if not u.is_cuda:
+            raise HyenaB200Error("HyenaOperator (hyena_b200) runs on CUDA sm_100a only; there is no CPU fallback")
+        in_dtype = u.dtype
+        u = u.to(torch.float32)
+        l = u.size(-2)
+        l_filter = min(l, self.l_max)
+        p = _InProj.apply(u, self.in_proj.weight)                                   # (B, 3D, l)
+        if l_filter < l:
+            p = p[..., :l_filter].contiguous()
+        k = self.filter_fn.filter_channel_major(l_filter)                           # (D, l_filter)
+        fb = self.filter_fn.bias if self.filter_fn.use_bias else 0 * self.filter_fn.bias
+        y_pre = ops.HyenaCoreFn.apply(p, self.in_proj.bias, self.short_filter.weight, self.short_filter.bias, k, fb)
+        y = _OutProj.apply(y_pre, self.out_proj.weight, self.out_proj.bias).to(in_dtype)
+        if self.return_state:
+            return y, None
+        return y
+
+    @property
+    def d_output(self):
+        return self.d_model

@@ -1,0 +1,213 @@
+"""Raw device ops (thin wrappers over the C ABI) and the autograd Functions built on them.
+
+PyTorch provides device memory, streams and autograd plumbing; all arithmetic of the custom-kernel
+span runs in libhyena_b200.so.  Inputs must be CUDA fp32 tensors -- anything else raises.
+"""
+import torch
+
+from . import _lib
+
+_ws_cache = {}
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _lib.HyenaB200Error("hyena_b200 ops need CUDA tensors (there is no CPU path)")
+        if t.dtype != torch.float32:
+            raise _lib.HyenaB200Error(f"hyena_b200 ops compute in fp32; got {t.dtype}")
+
+
+def workspace(B, D, L, backward, device):
+    """Cached scratch buffer for the FFT passes (one per device / shape class)."""
+    n = int(_lib.lib().hyena_b200_workspace_bytes(B, D, L, int(backward)))
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(n, dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def spectrum_elems(L):
+    return int(_lib.lib().hyena_b200_spectrum_elems(int(L)))
+
+
+# ------------------------------------------------------------------------------------------ filter
+def _filter_args(z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, shift, modulate, L):
+    E = z.shape[-1]
+    N = W1.shape[0]
+    D = W3.shape[0]
+    zz = z[0, :L] if z.dim() == 3 else z[:L]
+    tt = (t[0, :L, 0] if t.dim() == 3 else t[:L]).contiguous()
+    if zz.stride(-1) != 1:
+        zz = zz.contiguous()
+    return zz, tt, E, N, D
+
+
+def filter_forward(z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, shift, modulate, L):
+    """k (D, L) channel-major == HyenaFilter.filter(L)[0].T  (hyena.py:229-238)."""
+    _need_cuda(z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas)
+    zz, tt, E, N, D = _filter_args(z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, shift, modulate, L)
+    k = torch.empty(D, L, dtype=torch.float32, device=z.device)
+    ws = [x.contiguous() for x in (W0, b0, W1, b1, W2, b2, W3)]
+    fr = freq.reshape(-1).contiguous()
+    dl = deltas.reshape(-1).contiguous()
+    with torch.cuda.device(z.device):
+        _lib.check(_lib.lib().hyena_b200_filter_fwd(
+            _ptr(zz), zz.stride(0), _ptr(tt), *[_ptr(w) for w in ws], _ptr(fr), _ptr(dl),
+            float(shift), int(bool(modulate)), int(L), E, N, D, _ptr(k), _stream()))
+    return k
+
+
+def filter_backward(z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, shift, modulate, L, dk, need_dz):
+    _need_cuda(z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, dk)
+    zz, tt, E, N, D = _filter_args(z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, shift, modulate, L)
+    ws = [x.contiguous() for x in (W0, b0, W1, b1, W2, b2, W3)]
+    fr = freq.reshape(-1).contiguous()
+    dl = deltas.reshape(-1).contiguous()
+    dk = dk.contiguous()
+    grads = [torch.zeros_like(w) for w in ws]
+    dfreq = torch.zeros_like(fr)
+    dz = torch.zeros(L, E, dtype=torch.float32, device=z.device) if need_dz else None
+    with torch.cuda.device(z.device):
+        _lib.check(_lib.lib().hyena_b200_filter_bwd(
+            _ptr(zz), zz.stride(0), _ptr(tt), *[_ptr(w) for w in ws], _ptr(fr), _ptr(dl),
+            float(shift), int(bool(modulate)), int(L), E, N, D, _ptr(dk),
+            *[_ptr(g) for g in grads], _ptr(dfreq), _ptr(dz), E, _stream()))
+    return grads, dfreq, dz
+
+
+class HyenaFilterFn(torch.autograd.Function):
+    """Differentiable implicit filter: parameters -> k (D, L)."""
+
+    @staticmethod
+    def forward(ctx, z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, shift, modulate, L):
+        ctx.save_for_backward(z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas)
+        ctx.cfg = (shift, modulate, L)
+        return filter_forward(z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, shift, modulate, L)
+
+    @staticmethod
+    def backward(ctx, dk):
+        z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas = ctx.saved_tensors
+        shift, modulate, L = ctx.cfg
+        if ctx.needs_input_grad[10]:
+            raise _lib.HyenaB200Error("gradients w.r.t. modulation deltas (modulation_lr != 0) are not implemented")
+        need_dz = ctx.needs_input_grad[0]
+        grads, dfreq, dz = filter_backward(z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, shift, modulate, L,
+                                           dk, need_dz)
+        gz = None
+        if need_dz:
+            gz = torch.zeros_like(z)
+            (gz[0, :L] if z.dim() == 3 else gz[:L]).copy_(dz)
+        return (gz, None, *grads, dfreq.reshape(freq.shape), None, None, None, None)
+
+
+# ------------------------------------------------------------------------------------------ spectrum / core
+def filter_spectrum(k):
+    """Opaque packed spectrum of k (D, L) -> (D, M) complex64 (replaces rfft(k, 2L)/2L, hyena.py:62)."""
+    _need_cuda(k)
+    k = k.contiguous()
+    D, L = k.shape
+    M = spectrum_elems(L)
+    spec = torch.empty(D, M, dtype=torch.complex64, device=k.device)
+    ws = workspace(1, D, L, False, k.device)
+    with torch.cuda.device(k.device):
+        _lib.check(_lib.lib().hyena_b200_filter_spectrum(_ptr(k), _ptr(spec), D, L, _ptr(ws), ws.numel(), _stream()))
+    return spec
+
+
+def core_forward(p, in_bias, sw, sb, kspec, fbias, save_c):
+    _need_cuda(p, in_bias, sw, sb, fbias)
+    B, C3, L = p.shape
+    D = C3 // 3
+    assert p.is_contiguous() and kspec.is_contiguous()
+    y = torch.empty(B, D, L, dtype=torch.float32, device=p.device)
+    c = torch.empty(B, D, L, dtype=torch.float32, device=p.device) if save_c else None
+    ws = workspace(B, D, L, False, p.device)
+    with torch.cuda.device(p.device):
+        _lib.check(_lib.lib().hyena_b200_core_fwd(
+            _ptr(p), _ptr(in_bias), _ptr(sw), _ptr(sb), _ptr(kspec), _ptr(fbias), _ptr(y), _ptr(c),
+            B, D, L, _ptr(ws), ws.numel(), _stream()))
+    return y, c
+
+
+def core_backward(dy_pre, p, in_bias, sw, sb, kspec, fbias, c_saved):
+    _need_cuda(dy_pre, p, in_bias, sw, sb, fbias, c_saved)
+    B, C3, L = p.shape
+    D = C3 // 3
+    dev = p.device
+    dy_pre = dy_pre.contiguous()
+    dp = torch.empty_like(p)
+    ds = torch.empty_like(p)
+    dk = torch.empty(D, L, dtype=torch.float32, device=dev)
+    dsw = torch.zeros(C3, 3, dtype=torch.float32, device=dev)
+    dsb = torch.zeros(C3, dtype=torch.float32, device=dev)
+    dfb = torch.zeros(D, dtype=torch.float32, device=dev)
+    dib = torch.zeros(C3, dtype=torch.float32, device=dev) if in_bias is not None else None
+    ws = workspace(B, D, L, True, dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().hyena_b200_core_bwd(
+            _ptr(dy_pre), _ptr(p), _ptr(in_bias), _ptr(sw), _ptr(sb), _ptr(kspec), _ptr(fbias), _ptr(c_saved),
+            _ptr(dp), _ptr(dk), _ptr(dsw), _ptr(dsb), _ptr(dfb), _ptr(dib), _ptr(ds),
+            B, D, L, _ptr(ws), ws.numel(), _stream()))
+    del ds
+    return dp, dk, dsw, dsb, dfb, dib
+
+
+class HyenaCoreFn(torch.autograd.Function):
+    """(p, in_bias, short filter, k, filter bias) -> y_pre (B, D, L); hyena.py:394-432 for order 2."""
+
+    @staticmethod
+    def forward(ctx, p, in_bias, sw, sb, k, fbias):
+        p = p.contiguous()
+        sw2 = sw.reshape(sw.shape[0], -1).contiguous()
+        sb = sb.contiguous(); fbias = fbias.contiguous()
+        ib = in_bias.contiguous() if in_bias is not None else None
+        kspec = filter_spectrum(k)
+        need = any(ctx.needs_input_grad)
+        y, c = core_forward(p, ib, sw2, sb, kspec, fbias, need)
+        ctx.save_for_backward(p, ib, sw2, sb, kspec, fbias, c)
+        ctx.sw_shape = sw.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        p, ib, sw2, sb, kspec, fbias, c = ctx.saved_tensors
+        dp, dk, dsw, dsb, dfb, dib = core_backward(dy, p, ib, sw2, sb, kspec, fbias, c)
+        return dp, dib, dsw.reshape(ctx.sw_shape), dsb, dk, dfb
+
+
+# ------------------------------------------------------------------------------------------ plain fftconv
+def fftconv_forward(u, kspec, Dvec):
+    _need_cuda(u, Dvec)
+    B, H, L = u.shape
+    out = torch.empty_like(u)
+    ws = workspace(B, H, L, False, u.device)
+    with torch.cuda.device(u.device):
+        _lib.check(_lib.lib().hyena_b200_fftconv_fwd(_ptr(u), _ptr(kspec), _ptr(Dvec), _ptr(out), B, H, L,
+                                                     _ptr(ws), ws.numel(), _stream()))
+    return out
+
+
+def fftconv_backward(dout, u, kspec, Dvec):
+    _need_cuda(dout, u, Dvec)
+    B, H, L = u.shape
+    du = torch.empty_like(u)
+    dk = torch.empty(H, L, dtype=torch.float32, device=u.device)
+    dD = torch.zeros(H, dtype=torch.float32, device=u.device)
+    ws = workspace(B, H, L, True, u.device)
+    with torch.cuda.device(u.device):
+        _lib.check(_lib.lib().hyena_b200_fftconv_bwd(_ptr(dout), _ptr(u), _ptr(kspec), _ptr(Dvec), _ptr(du), _ptr(dk),
+                                                     _ptr(dD), B, H, L, _ptr(ws), ws.numel(), _stream()))
+    return du, dk, dD

@@ -1,0 +1,120 @@
+/* hyena_b200 -- C ABI of the sm_100a Hyena long-convolution library (libhyena_b200.so).
+ *
+ * This is the drop-in boundary for the HyenaOperator hot path of HazyResearch/hyena-dna.  The
+ * reference's own FFI for this path is the pybind11 module `fftconv`
+ * (csrc/fftconv/fftconv.cpp:238-241: fftconv_fwd / fftconv_bwd) called from
+ * src/ops/fftconv.py:58-108, plus the PyTorch graph of src/models/sequence/hyena.py:388-444.
+ * Every entry point below names the reference interface it replaces.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers (fp32, contiguous, 8-byte aligned unless stated); sizes are
+ *     element counts; `stream` is a cudaStream_t passed as void*.
+ *   - inputs are borrowed and never written; outputs are fully overwritten unless marked (+=).
+ *   - every function returns 0 on success and a non-zero code on failure; the message of the last
+ *     failure on the calling thread is returned by hyena_b200_last_error().  Nothing here falls
+ *     back to a CPU path: without a CUDA device the calls fail.
+ *   - the functions are stateless and re-entrant apart from a per-device table of FFT twiddles that
+ *     is built on first use; they enqueue work on `stream` and return without synchronising.
+ *   - sequence length limit: L <= hyena_b200_max_seqlen() (= 2^20).  The reference extension stops at
+ *     L <= 8192 (csrc/fftconv/fftconv.cpp:114-115).
+ *
+ * Layouts (B batch, D channels = d_model, L positions, N = filter_order = 64, E = emb_dim)
+ *   p      (B, 3D, L)  in_proj output, channel-major, WITHOUT in_proj.bias (passed separately);
+ *                      channels [0,D) = x0, [D,2D) = x1, [2D,3D) = v   (hyena.py:404)
+ *   k      (D, L)      time-domain filter, channel-major
+ *   kspec  (D, M) complex64 (interleaved re,im), M = hyena_b200_spectrum_elems(L): packed half-size
+ *                      spectrum of k in the library's internal [k1][k2] order -- opaque to callers
+ *   y_pre  (B, D, L)   operator output before out_proj, channel-major (hyena.py:432 before the rearrange)
+ */
+#ifndef HYENA_B200_H
+#define HYENA_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HYENA_B200_ABI_VERSION 1
+#if defined(__GNUC__)
+#define HY_API __attribute__((visibility("default")))
+#else
+#define HY_API
+#endif
+
+HY_API int hyena_b200_abi_version(void);
+HY_API const char* hyena_b200_last_error(void);
+/* number of CUDA kernels this library has launched since it was loaded (all threads) */
+HY_API unsigned long long hyena_b200_launch_count(void);
+HY_API int hyena_b200_max_seqlen(void);
+
+/* M: complex elements per channel of a filter spectrum for sequence length L (power of two >= L, >= 1024) */
+HY_API size_t hyena_b200_spectrum_elems(int L);
+/* scratch bytes the conv entry points want for (B, D, L); backward != 0 for the *_bwd calls.
+ * Any size >= hyena_b200_workspace_min_bytes() works; more lets more rows be in flight per launch. */
+HY_API size_t hyena_b200_workspace_bytes(int B, int D, int L, int backward);
+HY_API size_t hyena_b200_workspace_min_bytes(int B, int D, int L, int backward);
+
+/* ---- implicit filter -------------------------------------------------------------------------
+ * replaces HyenaFilter.filter (src/models/sequence/hyena.py:229-238): PositionalEmbedding rows
+ * z (L,E; row stride z_stride) and t (L), Sin-MLP (hyena.py:96-106, :199-215), ExponentialModulation
+ * (hyena.py:152-155).  Output k (D, L) channel-major == filter(L)[0].transpose(0,1).
+ * N (filter_order) must be 64; E odd in [3,15]. */
+HY_API int hyena_b200_filter_fwd(const float* z, int z_stride, const float* t,
+                          const float* W0, const float* b0, const float* W1, const float* b1,
+                          const float* W2, const float* b2, const float* W3,
+                          const float* freq, const float* deltas, float shift, int modulate,
+                          int L, int E, int N, int D, float* k_out, void* stream);
+
+/* autograd of the above (the reference relies on torch autograd; closed form restated in DESIGN.md).
+ * dk (D,L) -> parameter grads, all (+=) so callers zero them; dz (L,E; row stride dz_stride) may be NULL. */
+HY_API int hyena_b200_filter_bwd(const float* z, int z_stride, const float* t,
+                          const float* W0, const float* b0, const float* W1, const float* b1,
+                          const float* W2, const float* b2, const float* W3,
+                          const float* freq, const float* deltas, float shift, int modulate,
+                          int L, int E, int N, int D, const float* dk,
+                          float* dW0, float* db0, float* dW1, float* db1, float* dW2, float* db2,
+                          float* dW3, float* dfreq, float* dz, int dz_stride, void* stream);
+
+/* ---- filter spectrum -------------------------------------------------------------------------
+ * replaces `k_f = torch.fft.rfft(k, n=fft_size) / fft_size` (hyena.py:62, src/ops/fftconv.py:65). */
+HY_API int hyena_b200_filter_spectrum(const float* k, float* kspec, int D, int L,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- fused operator core ---------------------------------------------------------------------
+ * replaces hyena.py:394-432 for order=2: short_filter (depthwise Conv1d k=3, :363-369,:394), split
+ * (:404), gate v*x1 (:420), fftconv_ref with bias skip term (:59-88 via :261), gate *x0 (:432).
+ *   sw (3D,3) = short_filter.weight[:,0,:], sb (3D) = short_filter.bias, in_bias (3D) = in_proj.bias
+ *   or NULL, fbias (D) = filter_fn.bias.  c_save (B,D,L) receives the fftconv output (needed by
+ *   core_bwd) when non-NULL. */
+HY_API int hyena_b200_core_fwd(const float* p, const float* in_bias, const float* sw, const float* sb,
+                        const float* kspec, const float* fbias,
+                        float* y_pre, float* c_save, int B, int D, int L,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* backward of core_fwd (closed form: hyena.py:43-56 FFTConvFuncv2.backward,
+ * csrc/fftconv/fftconv_cuda.cu:1157-1179).  dy_pre (B,D,L).  Outputs: dp (B,3D,L), dk (D,L);
+ * (+=): dsw (3D,3), dsb (3D), dfbias (D), d_in_bias (3D, may be NULL).
+ * ds_scratch (B,3D,L) is caller-provided scratch for the short-filter output grads. */
+HY_API int hyena_b200_core_bwd(const float* dy_pre, const float* p, const float* in_bias, const float* sw,
+                        const float* sb, const float* kspec, const float* fbias, const float* c_saved,
+                        float* dp, float* dk, float* dsw, float* dsb, float* dfbias, float* d_in_bias,
+                        float* ds_scratch, int B, int D, int L,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- plain long convolution (the reference extension's own surface) ---------------------------
+ * fftconv_fwd replaces csrc/fftconv/fftconv.cpp:53-132 for fp32, gelu=false, no dropout mask, no q/v,
+ * head_dim=1:  out[b,h,:] = causal_conv(u[b,h,:], k[h,:]) + u[b,h,:] * Dvec[h]     (fftconv_ref,
+ * src/ops/fftconv.py:15-34).  The filter is passed as the opaque kspec from hyena_b200_filter_spectrum.
+ * fftconv_bwd replaces fftconv.cpp:134-236 + src/ops/fftconv.py:87-103: du (B,H,L), dk (H,L) time
+ * domain (the reference returns dk_f and inverts it in Python), dD (H) (+=). */
+HY_API int hyena_b200_fftconv_fwd(const float* u, const float* kspec, const float* Dvec, float* out,
+                           int B, int H, int L, void* workspace, size_t workspace_bytes, void* stream);
+HY_API int hyena_b200_fftconv_bwd(const float* dout, const float* u, const float* kspec, const float* Dvec,
+                           float* du, float* dk, float* dD, int B, int H, int L,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYENA_B200_H */

@@ -1,0 +1,262 @@
+"""GPU parity tests: the sm_100a path (through the C ABI) against the CPU oracle and the committed
+reference-generated golden vectors.  Tolerance from BASELINE.json north_star: 1e-3 rel / 1e-5 abs
+in fp32 (applied elementwise, with the abs term scaled by the tensor's magnitude where outputs are
+far from unit scale -- see SURVEY.md S8(c) for why)."""
+import math
+
+import pytest
+import torch
+
+from oracle import hyena_oracle as O
+from tests.golden_util import CASES, load
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-3, 1e-5
+
+
+def _dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return torch.device("cuda:0")
+
+
+def _close(got, ref, what, rtol=RTOL, atol=ATOL, scale_abs=True):
+    got = got.detach().double().cpu()
+    ref = ref.detach().double().cpu()
+    assert got.shape == ref.shape, f"{what}: shape {tuple(got.shape)} vs {tuple(ref.shape)}"
+    s = max(float(ref.abs().max()), 1e-30) if scale_abs else 1.0
+    a = atol * max(1.0, s) if scale_abs else atol
+    err = (got - ref).abs()
+    tol = a + rtol * ref.abs()
+    bad = err > tol
+    if bad.any():
+        # tolerate a vanishing fraction of cancellation-dominated elements as long as
+        # the normwise error is at fp32-FFT level
+        frac = float(bad.double().mean())
+        nrm = float(err.norm() / max(float(ref.norm()), 1e-30))
+        assert frac <= 1e-5 and nrm <= 1e-5, (
+            f"{what}: {int(bad.sum())} / {bad.numel()} elements out of tolerance (frac {frac:.2e}), "
+            f"max err {float(err.max()):.3e}, normwise rel {nrm:.3e}")
+
+
+def _module_from_sd(sd, D, l_max, E, w, dev, **kw):
+    import hyena_dna_b200 as H
+    op = H.HyenaOperator(D, l_max, order=2, filter_order=64, emb_dim=E, w=w, lr_pos_emb=kw.pop("lr_pos_emb", 0.0),
+                         layer_idx=0, device=None, dtype=None, **kw)
+    missing, unexpected = op.load_state_dict(sd, strict=True)
+    return op.to(dev)
+
+
+# ------------------------------------------------------------------------------------------ library
+def test_library_loads_and_counts_launches():
+    import hyena_dna_b200 as H
+    dev = _dev()
+    n0 = H.launch_count()
+    k = torch.randn(4, 256, device=dev)
+    H.ops.filter_spectrum(k)
+    torch.cuda.synchronize()
+    assert H.launch_count() > n0
+
+
+# ------------------------------------------------------------------------------------------ plain fftconv
+@pytest.mark.parametrize("L", [16, 250, 1001, 1024, 2048, 3000, 4096, 8192, 16384, 32768, 65536, 100000, 160000,
+                               262144, 524288, 1048576])
+def test_fftconv_func_forward_backward(L):
+    import hyena_dna_b200 as H
+    dev = _dev()
+    B, Hc = (2, 3) if L <= 262144 else (1, 2)
+    g = torch.Generator().manual_seed(L)
+    u = torch.randn(B, Hc, L, generator=g)
+    # decaying filter with unit-ish gain so outputs stay near unit scale (like a trained Hyena filter)
+    k = torch.randn(Hc, L, generator=g) * torch.exp(-torch.arange(L) / (0.05 * L + 1))[None] / math.sqrt(0.05 * L + 1)
+    Dv = torch.randn(Hc, generator=g)
+    dout = torch.randn(B, Hc, L, generator=g)
+    ur, kr, Dr = (x.double().clone().requires_grad_(True) for x in (u, k, Dv))
+    ref = O.fftconv_ref(ur, kr, Dr)
+    ref.backward(dout.double())
+    ug, kg, Dg = (x.to(dev).requires_grad_(True) for x in (u, k, Dv))
+    out = H.fftconv_func(ug, kg, Dg, gelu=False)
+    out.backward(dout.to(dev))
+    _close(out, ref, f"fftconv out L={L}")
+    _close(ug.grad, ur.grad, f"fftconv du L={L}")
+    _close(kg.grad, kr.grad, f"fftconv dk L={L}")
+    _close(Dg.grad, Dr.grad, f"fftconv dD L={L}", rtol=2e-3)
+
+
+def test_fftconv_impulse_and_linearity_full_length():
+    """Size-independent properties at L = 2^20: an impulse returns the filter; the op is linear in u."""
+    import hyena_dna_b200 as H
+    dev = _dev()
+    L, Hc = 1 << 20, 4
+    g = torch.Generator().manual_seed(7)
+    k = (torch.randn(Hc, L, generator=g) * torch.exp(-torch.arange(L) / 50000.0)[None]).to(dev)
+    Dv = torch.zeros(Hc, device=dev)
+    u = torch.zeros(1, Hc, L, device=dev)
+    shift = 12345
+    u[:, :, shift] = 1.0
+    out = H.fftconv_func(u, k, Dv, gelu=False)
+    expect = torch.zeros_like(out)
+    expect[0, :, shift:] = k[:, : L - shift]
+    _close(out, expect, "impulse response")
+    assert float(out[0, :, :shift].abs().max()) < 1e-4          # causal: nothing before the impulse
+    a = torch.randn(1, Hc, L, generator=g).to(dev)
+    b = torch.randn(1, Hc, L, generator=g).to(dev)
+    lhs = H.fftconv_func(2.0 * a - 3.0 * b, k, Dv, gelu=False)
+    rhs = 2.0 * H.fftconv_func(a, k, Dv, gelu=False) - 3.0 * H.fftconv_func(b, k, Dv, gelu=False)
+    _close(lhs, rhs, "linearity")
+
+
+def test_fftconv_rejects_unsupported_and_cpu():
+    import hyena_dna_b200 as H
+    dev = _dev()
+    u = torch.randn(1, 2, 64, device=dev); k = torch.randn(2, 64, device=dev); D = torch.randn(2, device=dev)
+    with pytest.raises(H.HyenaB200Error):
+        H.fftconv_func(u, k, D, gelu=True)
+    with pytest.raises(H.HyenaB200Error):
+        H.fftconv_func(u.cpu(), k.cpu(), D.cpu(), gelu=False)
+    with pytest.raises(H.HyenaB200Error):
+        H.ops.fftconv_forward(torch.randn(1, 1, (1 << 20) + 2, device=dev), torch.empty(1, 1 << 21, dtype=torch.complex64, device=dev),
+                              torch.zeros(1, device=dev))
+
+
+# ------------------------------------------------------------------------------------------ filter
+@pytest.mark.parametrize("case", CASES)
+def test_filter_matches_oracle(case):
+    import hyena_dna_b200 as H
+    dev = _dev()
+    G = load(case)
+    P = O.canonical(G["sd"])
+    L = G["L"]
+    ref = O.hyena_filter(L, O.to_dtype(P, torch.float64))[0].transpose(0, 1)
+    op = _module_from_sd(G["sd"], G["D"], G["l_max"], G["E"], G["w"], dev)
+    k = op.filter_fn.filter_channel_major(L)
+    _close(k, ref, f"filter {case}", scale_abs=False)
+    k3 = op.filter_fn.filter(L)
+    assert tuple(k3.shape) == (1, L, G["D"])
+
+
+def test_filter_backward_matches_oracle_including_z():
+    import hyena_dna_b200 as H
+    dev = _dev()
+    D, L, E = 24, 333, 5
+    g = torch.Generator().manual_seed(3)
+    P = O.init_params(D, L, emb_dim=E, w=10.0, generator=g)
+    dk = torch.randn(D, L, generator=g)
+    names = [k for k in P if "implicit_filter" in k] + ["filter_fn.pos_emb.z"]
+    Q = {k: v.double().clone().requires_grad_(k in names) for k, v in P.items()}
+    kref = O.hyena_filter(L, Q)[0].transpose(0, 1)
+    kref.backward(dk.double())
+    f = H.HyenaFilter(D, emb_dim=E, order=64, seq_len=L, w=10.0, lr_pos_emb=1e-5).to(dev)
+    sd = {k[len("filter_fn."):]: v for k, v in P.items() if k.startswith("filter_fn.")}
+    for extra in ("implicit_filter.3.freq", "implicit_filter.5.freq"):
+        sd[extra] = sd["implicit_filter.1.freq"]
+    f.load_state_dict(sd)
+    k = f.filter_channel_major(L)
+    k.backward(dk.to(dev))
+    _close(k, kref, "filter fwd", scale_abs=False)
+    got = dict(f.named_parameters())
+    for name in names:
+        short = name[len("filter_fn."):]
+        _close(got[short].grad, Q[name].grad, f"grad {short}", rtol=2e-3, atol=2e-5)
+
+
+# ------------------------------------------------------------------------------------------ operator
+@pytest.mark.parametrize("case", CASES)
+def test_operator_matches_reference_golden(case):
+    dev = _dev()
+    G = load(case)
+    op = _module_from_sd(G["sd"], G["D"], G["l_max"], G["E"], G["w"], dev)
+    u = G["u"].to(dev).requires_grad_(True)
+    y = op(u)
+    y.backward(G["dy"].to(dev))
+    _close(y, G["y"], f"{case} y")
+    _close(u.grad, G["du"], f"{case} du")
+    got = dict(op.named_parameters())
+    for name, gref in G["grad"].items():
+        _close(got[name].grad, gref, f"{case} grad {name}", rtol=2e-3, atol=2e-5)
+
+
+@pytest.mark.parametrize("B,L,D,l_max", [(2, 1001, 8, 1001), (1, 5000, 16, 8192), (2, 32768, 16, 32768),
+                                         (1, 160000, 8, 160000)])
+def test_operator_matches_oracle_fp64(B, L, D, l_max):
+    dev = _dev()
+    g = torch.Generator().manual_seed(B * 1000 + D)
+    P = O.init_params(D, l_max, emb_dim=5, w=10.0, generator=g, init_std=0.02)
+    u, _ = O.nucleotide_activations(B, L, D, seed=2222)
+    dy = torch.randn(B, L, D, generator=torch.Generator().manual_seed(1))
+    y64, du64, g64 = O.operator_fwd_bwd(u.double(), O.to_dtype(P, torch.float64), dy.double())
+    sd = dict(P)
+    for extra in ("filter_fn.implicit_filter.3.freq", "filter_fn.implicit_filter.5.freq"):
+        sd[extra] = sd["filter_fn.implicit_filter.1.freq"]
+    op = _module_from_sd(sd, D, l_max, 5, 10.0, dev)
+    ug = u.to(dev).requires_grad_(True)
+    y = op(ug)
+    y.backward(dy.to(dev))
+    _close(y, y64, "y")
+    _close(ug.grad, du64, "du")
+    got = dict(op.named_parameters())
+    for name, gref in g64.items():
+        _close(got[name].grad, gref, f"grad {name}", rtol=2e-3, atol=2e-5)
+
+
+def test_operator_large_1m_sampled_channels():
+    """large-1m shape on the sequence axis (L = 2^20) with a narrow model so the fp64 oracle stays fast."""
+    dev = _dev()
+    B, L, D = 1, 1 << 20, 8
+    g = torch.Generator().manual_seed(11)
+    P = O.init_params(D, L, emb_dim=5, w=10.0, generator=g, init_std=0.02)
+    u, _ = O.nucleotide_activations(B, L, D, seed=2222)
+    dy = torch.randn(B, L, D, generator=torch.Generator().manual_seed(1))
+    y64, du64, g64 = O.operator_fwd_bwd(u.double(), O.to_dtype(P, torch.float64), dy.double())
+    sd = dict(P)
+    for extra in ("filter_fn.implicit_filter.3.freq", "filter_fn.implicit_filter.5.freq"):
+        sd[extra] = sd["filter_fn.implicit_filter.1.freq"]
+    op = _module_from_sd(sd, D, L, 5, 10.0, dev)
+    ug = u.to(dev).requires_grad_(True)
+    y = op(ug)
+    y.backward(dy.to(dev))
+    _close(y, y64, "y 1m")
+    _close(ug.grad, du64, "du 1m")
+    got = dict(op.named_parameters())
+    for name in ("filter_fn.bias", "short_filter.weight", "filter_fn.implicit_filter.6.weight", "in_proj.bias"):
+        _close(got[name].grad, g64[name], f"grad {name} 1m", rtol=3e-3, atol=3e-5)
+
+
+def test_operator_full_width_large_1m_runs_and_is_causal():
+    """BASELINE.json configs[3] (L=1,048,576, d_model=256, batch=1): finite outputs + causality property."""
+    dev = _dev()
+    import hyena_dna_b200 as H
+    torch.manual_seed(0)
+    L, D = 1 << 20, 256
+    op = H.HyenaOperator(D, L, emb_dim=5, w=10, lr_pos_emb=0.0).to(dev)
+    u, _ = O.nucleotide_activations(1, L, D)
+    u = u.to(dev)
+    with torch.no_grad():
+        y0 = op(u)
+        u2 = u.clone()
+        cut = 700_001
+        u2[:, cut:] += 1.0
+        y1 = op(u2)
+    assert torch.isfinite(y0).all()
+    scale = float(y0.abs().max())
+    assert float((y0[:, :cut] - y1[:, :cut]).abs().max()) <= 2e-4 * max(scale, 1.0)
+    assert float((y0[:, cut:] - y1[:, cut:]).abs().max()) > 1e-3 * scale
+    u.requires_grad_(True)
+    y = op(u)
+    y.square().mean().backward()
+    assert torch.isfinite(u.grad).all()
+    for n, p in op.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
+
+
+def test_state_dict_roundtrip_and_optim_attrs():
+    import hyena_dna_b200 as H
+    G = load("ref_L64_D8")
+    op = H.HyenaOperator(G["D"], G["l_max"], emb_dim=G["E"], w=G["w"], lr=6e-4, lr_pos_emb=0.0)
+    assert set(op.state_dict().keys()) == set(G["sd"].keys())
+    for k, v in op.state_dict().items():
+        assert tuple(v.shape) == tuple(G["sd"][k].shape), k
+    assert op.filter_fn.implicit_filter[0].weight._optim == {"weight_decay": 0, "lr": 6e-4}
+    assert H.registry.layer["hyena"] is H.HyenaOperator
