@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- nucleotides/s through HyenaOperator fwd+bwd at L=1,048,576, d_model=256 (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's sm_100a path
+    python bench.py --impl reference [--steps K] [--warmup W]      # the reference's CPU torch.fft path
+
+A "step" is one forward + backward of the operator over one batch of synthetic single-nucleotide
+activations (B = 1 sample of L tokens per GPU: BASELINE.json configs[3]/[4]; weak scaling, global
+batch = N).  With N > 1 the driver launches one rank per GPU under torchrun; ranks are batch-sharded
+replicas and the only collective is the all-reduce of the operator's parameter grads (NCCL).
+
+One JSON line on stdout (rank 0).  Keys beyond the base contract:
+  roofline      HBM roofline of the custom-kernel span ((44+16/B)*D bytes per
+                nucleotide fwd+bwd, in_proj output -> out_proj input), achieved = those bytes / the
+                summed CUDA-event time of this library's kernels inside the timed steps; "kernels"
+                lists each kernel class' share so it can be checked against profiles/*launches*.csv
+  cpu_baseline  the oracle (CPU restatement of the reference torch.fft path) timed on the host cores
+                on a bounded sample of the same workload
+  e2e           same metric through the public module API with HOST (pinned) buffers: u and dy are
+                copied host->device and y, du and all parameter grads device->host inside the timed
+                region, copies overlapped with compute on a side stream where the data flow allows
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+L_FULL, D_MODEL, EMB, W_FREQ = 1 << 20, 256, 5, 10.0
+METRIC = "nucleotides/sec through HyenaOperator fwd+bwd at L=1M d=256"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--seqlen", type=int, default=L_FULL, help="override L (debug only; invalidates the number)")
+    ap.add_argument("--d-model", type=int, default=D_MODEL)
+    ap.add_argument("--batch", type=int, default=1, help="samples per GPU")
+    ap.add_argument("--cpu-sample-len", type=int, default=1 << 18,
+                    help="sequence length of the bounded CPU sample (cpu_baseline / reference arm)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_run(L, D, B, steps, warmup):
+    """Time the oracle (reference torch.fft path restated, fp32, all host threads) on CPU."""
+    from oracle import hyena_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(0)
+    P = O.init_params(D, L, emb_dim=EMB, w=W_FREQ, generator=g, init_std=0.02)
+    u, _ = O.nucleotide_activations(B, L, D)
+    dy = torch.randn(B, L, D, generator=g)
+    for _ in range(warmup):
+        O.operator_fwd_bwd(u, P, dy)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.operator_fwd_bwd(u, P, dy)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return {"value": B * L / dt, "unit": "nt/s", "cores": cores, "kind": "port",
+            "sample": f"oracle fwd+bwd, fp32 torch CPU, B={B} L={L} D={D}, {steps} step(s) after {warmup} warm-up "
+                      f"({dt:.2f} s/step)"}, dt
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    Ls = min(args.cpu_sample_len, args.seqlen)
+    cb, dt = cpu_reference_run(Ls, args.d_model, 1, args.steps, min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "nt/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"large-1m HyenaOperator fwd+bwd, bounded CPU sample L={Ls} d_model={args.d_model} "
+                                   f"batch=1 (per-nt cost of the full L=1,048,576 is ~log-factor higher)",
+                       "l2": "n/a (CPU)"},
+            "cpu_baseline": cb, "gpu_launches": 0,
+            "e2e": {"value": cb["value"], "unit": "nt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------- GPU arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import hyena_dna_b200 as H
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path for the product arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+    L, D, B = args.seqlen, args.d_model, args.batch
+    from oracle import hyena_oracle as O   # only for the synthetic-input recipe and the cpu_baseline leg
+    torch.manual_seed(1234)
+    op = H.HyenaOperator(D, L, order=2, filter_order=64, emb_dim=EMB, w=W_FREQ, lr_pos_emb=0.0)
+    # model-realistic init (standalone_hyenadna.py:612-641): Linear weights N(0, 0.02), biases 0
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        for m in op.modules():
+            if isinstance(m, torch.nn.Linear):
+                m.weight.copy_(torch.randn(m.weight.shape, generator=g) * 0.02)
+                if m.bias is not None:
+                    m.bias.zero_()
+        op.out_proj.weight.copy_(torch.randn(D, D, generator=g) * 0.02 / 4.0)
+    op = op.to(dev)
+    params = [p for p in op.parameters() if p.requires_grad]
+    u_host, _ = O.nucleotide_activations(B, L, D, seed=2222 + rank)
+    dy_host = torch.randn(B, L, D, generator=torch.Generator().manual_seed(1 + rank))
+    u_host, dy_host = u_host.pin_memory(), dy_host.pin_memory()
+    u = u_host.to(dev).requires_grad_(True)
+    dy = dy_host.to(dev)
+
+    def step():
+        for p in params:
+            p.grad = None
+        u.grad = None
+        y = op(u)
+        y.backward(dy)
+        if world > 1:
+            H.distributed.allreduce_grads(params)
+        return y
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    # ---------------- timed region (device-resident inputs)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = H.launch_count()
+    H._lib.profile_begin()
+    barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(); barrier()
+    ms = e0.elapsed_time(e1)
+    prof = H._lib.profile_end()
+    launches = H.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = world * B * L / (ms_step * 1e-3)
+
+    # ---------------- roofline of the custom-kernel span (rank 0's kernels)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    span_bytes = (44.0 + 16.0 / B) * D * B * L               # SURVEY.md S8(d), per step
+    span_ms = sum(v[0] for v in prof.values()) / args.steps
+    achieved = span_bytes / (span_ms * 1e-3) / 1e9 if span_ms > 0 else 0.0
+    kernels = {k: {"ms_per_step": round(v[0] / args.steps, 4), "launches_per_step": v[1] / args.steps,
+                   "share_of_span": round(v[0] / max(sum(x[0] for x in prof.values()), 1e-9), 4)}
+               for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+    roofline = {"bound": "hbm", "kernel": "custom-kernel span (in_proj output -> out_proj input), fwd+bwd, per step",
+                "achieved": round(achieved, 1), "peak": peak_gbs, "unit": "GB/s",
+                "frac": round(achieved / peak_gbs, 4), "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_step": span_bytes, "span_ms_per_step": round(span_ms, 4),
+                "step_ms": round(ms_step, 4), "kernels": kernels}
+
+    # ---------------- e2e: host buffers in, host buffers out
+    e2e = None
+    if not args.no_e2e:
+        y_host = torch.empty(B, L, D).pin_memory()
+        du_host = torch.empty(B, L, D).pin_memory()
+        g_host = [torch.empty(p.shape).pin_memory() for p in params]
+        side = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream()
+        u_dev = torch.empty(B, L, D, device=dev)
+        dy_dev = torch.empty(B, L, D, device=dev)
+
+        def e2e_step():
+            for p in params:
+                p.grad = None
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                u_dev.copy_(u_host, non_blocking=True)
+                ev_u = torch.cuda.Event(); ev_u.record(side)
+                dy_dev.copy_(dy_host, non_blocking=True)          # overlaps the forward
+                ev_dy = torch.cuda.Event(); ev_dy.record(side)
+            main.wait_event(ev_u)
+            uu = u_dev.detach().requires_grad_(True)
+            y = op(uu)
+            ev_y = torch.cuda.Event(); ev_y.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ev_y)
+                y_host.copy_(y.detach(), non_blocking=True)       # overlaps the backward
+            main.wait_event(ev_dy)
+            y.backward(dy_dev)
+            if world > 1:
+                H.distributed.allreduce_grads(params)
+            du_host.copy_(uu.grad, non_blocking=True)
+            for gh, p in zip(g_host, params):
+                gh.copy_(p.grad, non_blocking=True)
+            main.wait_stream(side)
+
+        for _ in range(2):
+            e2e_step()
+        torch.cuda.synchronize(); barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        a1.record()
+        torch.cuda.synchronize(); barrier()
+        t2 = torch.tensor([a0.elapsed_time(a1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t2.item()) / args.steps
+        pbytes = sum(p.numel() for p in params) * 4
+        e2e = {"value": world * B * L / (e2e_ms * 1e-3), "unit": "nt/s", "ms_per_step": round(e2e_ms, 3),
+               "h2d_bytes_per_step": 2 * B * L * D * 4, "d2h_bytes_per_step": 2 * B * L * D * 4 + pbytes,
+               "note": "per GPU; u,dy pinned host -> device; y, du, param grads device -> pinned host; "
+                       "dy upload overlaps forward, y download overlaps backward"}
+
+    # ---------------- CPU baseline (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu, _ = cpu_reference_run(min(args.cpu_sample_len, L), D, 1, 1, 1)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "nt/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"large-1m: HyenaOperator fwd+bwd, L={L} d_model={D} order=2 filter_order=64 "
+                                       f"emb_dim={EMB}, batch {B}/GPU (global {world * B}), fp32, TF32 off",
+                           "parallelism": f"dp{world} (batch-sharded replicas, grad all-reduce)",
+                           "l2": "inputs larger than L2 (u, p, dy are 1-3 GB each; 126 MB L2), no explicit flush"},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "impl": "b200"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -24,6 +24,9 @@ SIGNATURES = {
     "hyena_b200_last_error": (ctypes.c_char_p, []),
     "hyena_b200_launch_count": (ctypes.c_ulonglong, []),
     "hyena_b200_max_seqlen": (_i, []),
+    "hyena_b200_profile_begin": (_i, []),
+    "hyena_b200_profile_end": (_i, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_ulonglong), _i]),
+    "hyena_b200_kind_name": (ctypes.c_char_p, [_i]),
     "hyena_b200_spectrum_elems": (_sz, [_i]),
     "hyena_b200_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "hyena_b200_workspace_min_bytes": (_sz, [_i, _i, _i, _i]),
@@ -81,3 +84,16 @@ def check(status):
 
 def launch_count():
     return int(lib().hyena_b200_launch_count())
+
+
+def profile_begin():
+    check(lib().hyena_b200_profile_begin())
+
+
+def profile_end():
+    """-> {kernel class: (device ms, launches)} for the window opened by profile_begin()."""
+    n = 16
+    ms = (ctypes.c_double * n)()
+    cnt = (ctypes.c_ulonglong * n)()
+    check(lib().hyena_b200_profile_end(ms, cnt, n))
+    return {lib().hyena_b200_kind_name(i).decode(): (ms[i], int(cnt[i])) for i in range(n) if cnt[i]}

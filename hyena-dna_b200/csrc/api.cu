@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "../../include/hyena_b200.h"
 #include "launch.h"
@@ -13,7 +14,37 @@ namespace hy {
 
 static thread_local char g_err[512] = "";
 static std::atomic<unsigned long long> g_launches{0};
-void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- optional per-launch event timing (bench.py's roofline leg); off by default
+struct ProfRec { int kind; cudaEvent_t e0, e1; };
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;            // records of the current profiling window
+static std::vector<cudaEvent_t> g_ev_pool;     // recycled events
+static thread_local cudaEvent_t g_cur_e0 = nullptr;
+
+static cudaEvent_t get_event() {
+  if (!g_ev_pool.empty()) { cudaEvent_t e = g_ev_pool.back(); g_ev_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+void prof_begin(int kind, cudaStream_t s) {
+  (void)kind;
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_cur_e0 = get_event();
+  cudaEventRecord(g_cur_e0, s);
+}
+void prof_end(int kind, cudaStream_t s) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (!g_prof_on || !g_cur_e0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEvent_t e1 = get_event();
+  cudaEventRecord(e1, s);
+  g_prof.push_back({kind, g_cur_e0, e1});
+  g_cur_e0 = nullptr;
+}
 
 static int fail(const char* fmt, ...) {
   va_list ap;
@@ -132,6 +163,40 @@ HY_API int hyena_b200_abi_version(void) { return HYENA_B200_ABI_VERSION; }
 HY_API const char* hyena_b200_last_error(void) { return g_err; }
 HY_API unsigned long long hyena_b200_launch_count(void) { return g_launches.load(); }
 HY_API int hyena_b200_max_seqlen(void) { return 1 << 20; }
+
+HY_API int hyena_b200_profile_begin(void) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof) { g_ev_pool.push_back(r.e0); g_ev_pool.push_back(r.e1); }
+  g_prof.clear();
+  g_prof_on = true;
+  return 0;
+}
+
+HY_API int hyena_b200_profile_end(double* ms_by_kind, unsigned long long* launches_by_kind, int n) {
+  HY_CHECK(ms_by_kind && launches_by_kind && n >= K_COUNT, "profile_end needs arrays of >= %d entries", K_COUNT);
+  HY_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = false;
+  for (int i = 0; i < n; ++i) { ms_by_kind[i] = 0.0; launches_by_kind[i] = 0; }
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    HY_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    ms_by_kind[r.kind] += ms;
+    launches_by_kind[r.kind] += 1;
+    g_ev_pool.push_back(r.e0); g_ev_pool.push_back(r.e1);
+  }
+  g_prof.clear();
+  return 0;
+}
+
+HY_API const char* hyena_b200_kind_name(int kind) {
+  static const char* names[K_COUNT] = {
+      "col_fwd<filter>", "col_fwd<gate>", "col_fwd<dc>", "col_fwd<plain>",
+      "col_inv<conv_fwd>", "col_inv<bwd_dg>", "col_inv<dk>", "col_inv<plain_fwd>", "col_inv<plain_bwd>",
+      "row_pass<filter>", "row_pass<conv_fwd>", "row_pass<conv_bwd>",
+      "filter_fwd", "filter_bwd", "short_conv_bwd", "twiddle_init"};
+  return (kind >= 0 && kind < K_COUNT) ? names[kind] : "?";
+}
 
 HY_API size_t hyena_b200_spectrum_elems(int L) { return L < 1 ? 0 : ((size_t)kM2 << log_m1_for(L)); }
 

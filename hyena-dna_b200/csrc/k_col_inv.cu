@@ -7,8 +7,9 @@ static cudaError_t go(const PassArgs& a, int rows, cudaStream_t s) {
   auto kern = col_inv_kernel<LOGM1, MODE>;
   cudaError_t e = set_smem(kern, CG::SMEM);
   if (e != cudaSuccess) return e;
+  prof_begin(K_COL_INV + MODE, s);
   kern<<<dim3(CG::CTAS, rows), CG::THREADS, CG::SMEM, s>>>(a);
-  count_launch();
+  prof_end(K_COL_INV + MODE, s);
   return cudaGetLastError();
 }
 

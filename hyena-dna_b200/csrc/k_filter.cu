@@ -15,8 +15,9 @@ __global__ void twiddle_init_kernel(float2* tw1024, float2* twlo) {
 }
 
 cudaError_t launch_twiddle_init(float2* tw1024, float2* twlo, cudaStream_t s) {
+  prof_begin(K_TWIDDLE, s);
   twiddle_init_kernel<<<4, 256, 0, s>>>(tw1024, twlo);
-  count_launch();
+  prof_end(K_TWIDDLE, s);
   return cudaGetLastError();
 }
 
@@ -24,8 +25,9 @@ cudaError_t launch_filter_fwd(const FilterParams& P, float* kout, cudaStream_t s
   const size_t smem = filter_fwd_smem(P.E);
   cudaError_t e = set_smem(filter_fwd_kernel, smem);
   if (e != cudaSuccess) return e;
+  prof_begin(K_FILTER_FWD, s);
   filter_fwd_kernel<<<(P.L + kFwdTP - 1) / kFwdTP, 256, smem, s>>>(P, kout);
-  count_launch();
+  prof_end(K_FILTER_FWD, s);
   return cudaGetLastError();
 }
 
@@ -38,15 +40,17 @@ cudaError_t launch_filter_bwd(const FilterParams& P, const float* dk, const Filt
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int ntiles = (P.L + kBwdTP - 1) / kBwdTP;
   const int grid = ntiles < sms ? ntiles : sms;
+  prof_begin(K_FILTER_BWD, s);
   filter_bwd_kernel<<<grid, 256, smem, s>>>(P, dk, G, ntiles);
-  count_launch();
+  prof_end(K_FILTER_BWD, s);
   return cudaGetLastError();
 }
 
 cudaError_t launch_short_bwd(const ShortBwdArgs& a, int B, cudaStream_t s) {
   dim3 grid((a.L + kScSpan - 1) / kScSpan, a.C3, B);
+  prof_begin(K_SHORT_BWD, s);
   short_conv_bwd_kernel<<<grid, 256, 0, s>>>(a);
-  count_launch();
+  prof_end(K_SHORT_BWD, s);
   return cudaGetLastError();
 }
 

@@ -13,8 +13,9 @@ static cudaError_t go(const PassArgs& a, int rows, cudaStream_t s) {
   auto kern = row_pass_kernel<MODE>;
   cudaError_t e = set_smem(kern, smem);
   if (e != cudaSuccess) return e;
+  prof_begin(K_ROW + MODE, s);
   kern<<<dim3(ctas, rows), nwarps * 32, smem, s>>>(a);
-  count_launch();
+  prof_end(K_ROW + MODE, s);
   return cudaGetLastError();
 }
 

@@ -6,7 +6,15 @@
 
 namespace hy {
 
-void count_launch();                       // api.cu
+// kernel classes for the launch counter / per-launch event timing (api.cu)
+enum Kind {
+  K_COL_FWD = 0,      // + ColMode  (0..3)
+  K_COL_INV = 4,      // + InvMode  (4..8)
+  K_ROW = 9,          // + RowMode  (9..11)
+  K_FILTER_FWD = 12, K_FILTER_BWD = 13, K_SHORT_BWD = 14, K_TWIDDLE = 15, K_COUNT = 16
+};
+void prof_begin(int kind, cudaStream_t s);     // api.cu: records an event when profiling is on
+void prof_end(int kind, cudaStream_t s);       // api.cu: records an event when profiling is on; counts the launch
 cudaError_t launch_col_fwd(int mode, const PassArgs& a, int rows, cudaStream_t s);
 cudaError_t launch_col_inv(int mode, const PassArgs& a, int rows, cudaStream_t s);
 cudaError_t launch_row_pass(int mode, const PassArgs& a, int rows, cudaStream_t s);

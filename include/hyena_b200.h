@@ -48,6 +48,13 @@ HY_API const char* hyena_b200_last_error(void);
 HY_API unsigned long long hyena_b200_launch_count(void);
 HY_API int hyena_b200_max_seqlen(void);
 
+/* Optional per-launch timing with CUDA events on the launching stream (used by bench.py's roofline leg).
+ * profile_begin() starts a window; profile_end() synchronises the device and returns, per kernel class
+ * (index < 16, name from hyena_b200_kind_name), the summed device milliseconds and the launch count. */
+HY_API int hyena_b200_profile_begin(void);
+HY_API int hyena_b200_profile_end(double* ms_by_kind, unsigned long long* launches_by_kind, int n);
+HY_API const char* hyena_b200_kind_name(int kind);
+
 /* M: complex elements per channel of a filter spectrum for sequence length L (power of two >= L, >= 1024) */
 HY_API size_t hyena_b200_spectrum_elems(int L);
 /* scratch bytes the conv entry points want for (B, D, L); backward != 0 for the *_bwd calls.
