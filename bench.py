@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--seqlen", type=int, default=L_FULL, help="override L (debug only; invalidates the number)")
     ap.add_argument("--d-model", type=int, default=D_MODEL)
     ap.add_argument("--batch", type=int, default=1, help="samples per GPU")
-    ap.add_argument("--cpu-sample-len", type=int, default=1 << 18,
+    ap.add_argument("--cpu-sample-len", type=int, default=1 << 16,
                     help="sequence length of the bounded CPU sample (cpu_baseline / reference arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -46,6 +46,13 @@ void prof_end(int kind, cudaStream_t s) {
   g_cur_e0 = nullptr;
 }
 
+int api_fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
 static int fail(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -95,11 +102,12 @@ static int log_m1_for(int L) {        // M = 1024 * 2^logM1 >= L
 static size_t row_bytes(int L) { return ((size_t)kM2 << log_m1_for(L)) * sizeof(float2); }
 
 static size_t group_budget_bytes() {
-  // scratch kept in flight per launch group; sized to stay resident in B200's 126 MB L2
+  // scratch rows in flight per launch group.  Measured on B200 (profiles/r1_group_sweep.txt): the passes are
+  // issue/latency bound, not HBM bound, so many waves per launch beat keeping the scratch L2-resident
   static size_t v = 0;
   if (!v) {
     const char* e = getenv("HYENA_B200_GROUP_MB");
-    long mb = e ? atol(e) : 32;
+    long mb = e ? atol(e) : 256;
     if (mb < 1) mb = 1;
     v = (size_t)mb << 20;
   }

@@ -38,14 +38,14 @@ __device__ __forceinline__ void load_window(const float* __restrict__ row, int t
                                             float (&P)[4]) {
   if (vec) {   // L even, row base 8-byte aligned, t0 even, t0 < L  =>  t0+1 < L
     float2 a = make_float2(0.f, 0.f);
-    if (t0 >= 2) { a = *reinterpret_cast<const float2*>(row + t0 - 2); a.x += ib; a.y += ib; }
-    float2 b = *reinterpret_cast<const float2*>(row + t0);
+    if (t0 >= 2) { a = __ldg(reinterpret_cast<const float2*>(row + t0 - 2)); a.x += ib; a.y += ib; }
+    float2 b = __ldg(reinterpret_cast<const float2*>(row + t0));
     P[0] = a.x; P[1] = a.y; P[2] = b.x + ib; P[3] = b.y + ib;
   } else {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int t = t0 - 2 + j;
-      P[j] = (t >= 0 && t < L) ? row[t] + ib : 0.f;
+      P[j] = (t >= 0 && t < L) ? __ldg(row + t) + ib : 0.f;
     }
   }
 }
@@ -60,9 +60,16 @@ __device__ __forceinline__ float2 conv_pair(const float* __restrict__ row, int t
   return r;
 }
 
+__device__ __forceinline__ float2 conv_window(const float (&P)[4], int t0, int L, const Taps& k) {
+  float2 r;
+  r.x = fmaf(k.w0, P[0], fmaf(k.w1, P[1], fmaf(k.w2, P[2], k.b)));
+  r.y = (t0 + 1 < L) ? fmaf(k.w0, P[1], fmaf(k.w1, P[2], fmaf(k.w2, P[3], k.b))) : 0.f;
+  return r;
+}
+
 __device__ __forceinline__ float2 load_pair(const float* __restrict__ row, int t0, int L, bool vec) {
-  if (vec) return *reinterpret_cast<const float2*>(row + t0);
-  return make_float2(row[t0], (t0 + 1 < L) ? row[t0 + 1] : 0.f);
+  if (vec) return __ldg(reinterpret_cast<const float2*>(row + t0));
+  return make_float2(__ldg(row + t0), (t0 + 1 < L) ? __ldg(row + t0 + 1) : 0.f);
 }
 __device__ __forceinline__ void store_pair(float* __restrict__ row, int t0, int L, bool vec, float2 v) {
   if (vec) { *reinterpret_cast<float2*>(row + t0) = v; return; }
@@ -237,33 +244,54 @@ struct InvCtx {
   float red;           // per-thread partial of the reduction this mode produces
 };
 
+// Everything pass 3 reads from HBM for one sample pair, loaded up front so that a batch of slots has all
+// its loads in flight before the first use (the epilogue is latency-bound otherwise).
+struct InvIn {
+  float P0[4], P1[4], P2[4];   // raw windows of the x0 / x1 / v rows of p
+  float2 a, b;                 // mode-specific extra operands
+};
+
+template <int MODE>
+__device__ __forceinline__ void inv_load(const PassArgs& a, const InvCtx& cx, int b, int c, int t0, bool vec, InvIn& in) {
+  const int L = a.L, D = a.D;
+  if constexpr (MODE == INV_PLAIN_FWD) {
+    in.a = load_pair(a.src + row_off(b, c, D, L), t0, L, vec);
+  } else if constexpr (MODE == INV_PLAIN_BWD) {
+    in.a = load_pair(a.src2 + row_off(b, c, D, L), t0, L, vec);
+    in.b = load_pair(a.src + row_off(b, c, D, L), t0, L, vec);
+  } else if constexpr (MODE == INV_CONV_FWD || MODE == INV_BWD_DG) {
+    load_window(a.p + row_off(b, c, 3 * D, L), t0, L, vec, cx.k0.ib, in.P0);
+    load_window(a.p + row_off(b, D + c, 3 * D, L), t0, L, vec, cx.k1.ib, in.P1);
+    load_window(a.p + row_off(b, 2 * D + c, 3 * D, L), t0, L, vec, cx.k2.ib, in.P2);
+    if constexpr (MODE == INV_BWD_DG) {
+      in.a = load_pair(a.src + row_off(b, c, D, L), t0, L, vec);
+      in.b = load_pair(a.src2 + row_off(b, c, D, L), t0, L, vec);
+    }
+  }
+}
+
 // y = (y[t0], y[t0+1]) already scaled
 template <int MODE>
-__device__ __forceinline__ void inv_output(const PassArgs& a, InvCtx& cx, int b, int c, int t0, bool vec, float2 y) {
+__device__ __forceinline__ void inv_finish(const PassArgs& a, InvCtx& cx, int b, int c, int t0, bool vec, float2 y,
+                                           const InvIn& in) {
   const int L = a.L, D = a.D;
   if constexpr (MODE == INV_DK) {
     store_pair(a.out + (size_t)c * L, t0, L, vec, y);
   } else if constexpr (MODE == INV_PLAIN_FWD) {       // out = y + u * D      hyena.py:82
-    float2 u = load_pair(a.src + row_off(b, c, D, L), t0, L, vec);
-    store_pair(a.out + row_off(b, c, D, L), t0, L, vec, make_float2(fmaf(u.x, cx.fb, y.x), fmaf(u.y, cx.fb, y.y)));
+    store_pair(a.out + row_off(b, c, D, L), t0, L, vec, make_float2(fmaf(in.a.x, cx.fb, y.x), fmaf(in.a.y, cx.fb, y.y)));
   } else if constexpr (MODE == INV_PLAIN_BWD) {       // du = corr + dout * D ; dD += dout * u
-    float2 d = load_pair(a.src2 + row_off(b, c, D, L), t0, L, vec);
-    float2 u = load_pair(a.src + row_off(b, c, D, L), t0, L, vec);
-    cx.red = fmaf(d.x, u.x, fmaf(d.y, u.y, cx.red));
-    store_pair(a.out + row_off(b, c, D, L), t0, L, vec, make_float2(fmaf(d.x, cx.fb, y.x), fmaf(d.y, cx.fb, y.y)));
+    cx.red = fmaf(in.a.x, in.b.x, fmaf(in.a.y, in.b.y, cx.red));
+    store_pair(a.out + row_off(b, c, D, L), t0, L, vec, make_float2(fmaf(in.a.x, cx.fb, y.x), fmaf(in.a.y, cx.fb, y.y)));
   } else if constexpr (MODE == INV_CONV_FWD) {        // c = y + bias*g ; y_pre = c * x0     hyena.py:82, :432
-    float2 x0 = conv_pair(a.p + row_off(b, c, 3 * D, L), t0, L, vec, cx.k0);
-    float2 x1 = conv_pair(a.p + row_off(b, D + c, 3 * D, L), t0, L, vec, cx.k1);
-    float2 vv = conv_pair(a.p + row_off(b, 2 * D + c, 3 * D, L), t0, L, vec, cx.k2);
+    const float2 x0 = conv_window(in.P0, t0, L, cx.k0), x1 = conv_window(in.P1, t0, L, cx.k1),
+                 vv = conv_window(in.P2, t0, L, cx.k2);
     float2 cc = make_float2(fmaf(x1.x * vv.x, cx.fb, y.x), fmaf(x1.y * vv.y, cx.fb, y.y));
     if (a.out2) store_pair(a.out2 + row_off(b, c, D, L), t0, L, vec, cc);
     store_pair(a.out + row_off(b, c, D, L), t0, L, vec, make_float2(cc.x * x0.x, cc.y * x0.y));
   } else {                                            // INV_BWD_DG
-    float2 x0 = conv_pair(a.p + row_off(b, c, 3 * D, L), t0, L, vec, cx.k0);
-    float2 x1 = conv_pair(a.p + row_off(b, D + c, 3 * D, L), t0, L, vec, cx.k1);
-    float2 vv = conv_pair(a.p + row_off(b, 2 * D + c, 3 * D, L), t0, L, vec, cx.k2);
-    float2 dy = load_pair(a.src + row_off(b, c, D, L), t0, L, vec);
-    float2 cs = load_pair(a.src2 + row_off(b, c, D, L), t0, L, vec);
+    const float2 x0 = conv_window(in.P0, t0, L, cx.k0), x1 = conv_window(in.P1, t0, L, cx.k1),
+                 vv = conv_window(in.P2, t0, L, cx.k2);
+    const float2 dy = in.a, cs = in.b;
     float2 dc = make_float2(dy.x * x0.x, dy.y * x0.y);
     float2 dg = make_float2(fmaf(dc.x, cx.fb, y.x), fmaf(dc.y, cx.fb, y.y));     // + bias * dc
     cx.red = fmaf(dc.x, x1.x * vv.x, fmaf(dc.y, x1.y * vv.y, cx.red));           // dbias += dc * g
@@ -271,6 +299,13 @@ __device__ __forceinline__ void inv_output(const PassArgs& a, InvCtx& cx, int b,
     store_pair(a.out2 + row_off(b, D + c, 3 * D, L), t0, L, vec, make_float2(dg.x * vv.x, dg.y * vv.y));       // d x1c
     store_pair(a.out2 + row_off(b, 2 * D + c, 3 * D, L), t0, L, vec, make_float2(dg.x * x1.x, dg.y * x1.y));   // d vc
   }
+}
+
+template <int MODE>
+__device__ __forceinline__ void inv_output(const PassArgs& a, InvCtx& cx, int b, int c, int t0, bool vec, float2 y) {
+  InvIn in;
+  inv_load<MODE>(a, cx, b, c, t0, vec, in);
+  inv_finish<MODE>(a, cx, b, c, t0, vec, y, in);
 }
 
 template <int LOGM1, int MODE>
@@ -307,15 +342,25 @@ col_inv_kernel(const PassArgs a) {
       v[n1] = Arow[(size_t)(CG::R2 * n1 + q) * kM2 + m2];
     });
     block_fft<CG::TWO ? LOGM1 : 5, true, false>(v, smem + col * CG::PITCH, q, a.T.tw1024, CtaSync{});
-    // only m1 < M1/2 (slots s < 16) can hold samples t < L
-    static_for<0, 16>([&](auto s_) {
-      constexpr int s = decltype(s_)::value;
-      const int m1 = CG::R2 * s + q;
-      const int t0 = 2 * (m1 * kM2 + m2);
-      if (t0 < L) {
-        float2 y = v[Geo<CG::TWO ? LOGM1 : 5>::slot(s)];
-        inv_output<MODE>(a, cx, b, c, t0, vec, make_float2(y.x * a.scale, y.y * a.scale));
-      }
+    // only m1 < M1/2 (slots s < 16) can hold samples t < L; slots are handled four at a time with all
+    // their loads issued before the first dependent instruction
+    constexpr int NB = (MODE == INV_DK) ? 1 : 4;
+    static_for<0, 16 / NB>([&](auto g_) {
+      constexpr int s0 = decltype(g_)::value * NB;
+      InvIn in[NB];
+      static_for<0, NB>([&](auto j_) {
+        constexpr int j = decltype(j_)::value;
+        const int t0 = 2 * ((CG::R2 * (s0 + j) + q) * kM2 + m2);
+        if (t0 < L) inv_load<MODE>(a, cx, b, c, t0, vec, in[j]);
+      });
+      static_for<0, NB>([&](auto j_) {
+        constexpr int j = decltype(j_)::value;
+        const int t0 = 2 * ((CG::R2 * (s0 + j) + q) * kM2 + m2);
+        if (t0 < L) {
+          float2 y = v[Geo<CG::TWO ? LOGM1 : 5>::slot(s0 + j)];
+          inv_finish<MODE>(a, cx, b, c, t0, vec, make_float2(y.x * a.scale, y.y * a.scale), in[j]);
+        }
+      });
     });
   } else {
     static_for<0, CG::G>([&](auto g_) {

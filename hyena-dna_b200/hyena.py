@@ -139,20 +139,42 @@ class HyenaFilter(OptimModule):
 
 
 class _InProj(torch.autograd.Function):
-    """p = W u^T written channel-major (B, 3D, L) straight from cuBLAS: no transpose pass
+    """p = W u^T written channel-major (B, 3D, L) straight from the GEMM: no transpose pass
     (replaces hyena.py:391-392).  The bias is added inside the fused kernels."""
 
     @staticmethod
     def forward(ctx, u, W):
+        u = u.contiguous(); W = W.contiguous()
         ctx.save_for_backward(u, W)
-        B = u.shape[0]
-        return torch.bmm(W.unsqueeze(0).expand(B, -1, -1), u.transpose(1, 2))
+        B, L, D = u.shape
+        C3 = W.shape[0]
+        if ops.gemm_mode() == "torch":
+            return torch.bmm(W.unsqueeze(0).expand(B, -1, -1), u.transpose(1, 2))
+        p = torch.empty(B, C3, L, dtype=torch.float32, device=u.device)
+        # col-major: P^T (L x 3D, ld L) = U (L x D) W^T (D x 3D);  U stored (D x L, ld D) -> op T
+        ops.gemm(1, 0, L, C3, D, u, D, L * D, W, D, 0, p, L, C3 * L, batch=B)
+        return p
 
     @staticmethod
     def backward(ctx, dp):
         u, W = ctx.saved_tensors
-        du = torch.matmul(dp.transpose(1, 2), W) if ctx.needs_input_grad[0] else None
-        dW = torch.bmm(dp, u).sum(0) if ctx.needs_input_grad[1] else None
+        B, L, D = u.shape
+        C3 = W.shape[0]
+        dp = dp.contiguous()
+        if ops.gemm_mode() == "torch":
+            du = torch.matmul(dp.transpose(1, 2), W) if ctx.needs_input_grad[0] else None
+            dW = torch.bmm(dp, u).sum(0) if ctx.needs_input_grad[1] else None
+            return du, dW
+        du = dW = None
+        if ctx.needs_input_grad[0]:
+            du = torch.empty_like(u)
+            # dU^T (D x L, ld D) = W^T (D x 3D, stored ld D, op N) dP (3D x L; stored (L x 3D, ld L) -> op T)
+            ops.gemm(0, 1, D, L, C3, W, D, 0, dp, L, C3 * L, du, D, L * D, batch=B)
+        if ctx.needs_input_grad[1]:
+            dW = torch.empty_like(W)
+            # dW^T (D x 3D, ld D) = sum_b U_b^T (D x L, stored, op N) dP_b^T (L x 3D, stored ld L, op N)
+            for b in range(B):
+                ops.gemm(0, 0, D, C3, L, u[b], D, 0, dp[b], L, 0, dW, D, 0, batch=1, beta=0.0 if b == 0 else 1.0)
         return du, dW
 
 
@@ -161,20 +183,45 @@ class _OutProj(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, y_pre, W, b):
+        y_pre = y_pre.contiguous(); W = W.contiguous()
         ctx.save_for_backward(y_pre, W)
-        B = y_pre.shape[0]
-        y = torch.bmm(y_pre.transpose(1, 2), W.t().unsqueeze(0).expand(B, -1, -1))
-        if b is not None:
-            y += b
+        ctx.has_bias = b is not None
+        B, C, L = y_pre.shape
+        Do = W.shape[0]
+        if ops.gemm_mode() == "torch":
+            y = torch.bmm(y_pre.transpose(1, 2), W.t().unsqueeze(0).expand(B, -1, -1))
+            if b is not None:
+                y += b
+            return y
+        y = torch.empty(B, L, Do, dtype=torch.float32, device=y_pre.device)
+        # Y^T (Do x L, ld Do) = W (Do x C; stored (C x Do, ld C) -> op T) Ypre (C x L; stored (L x C, ld L) -> op T)
+        ops.gemm(1, 1, Do, L, C, W, C, 0, y_pre, L, C * L, y, Do, L * Do, batch=B,
+                 bias=b.contiguous() if b is not None else None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         y_pre, W = ctx.saved_tensors
-        B = dy.shape[0]
-        d_pre = torch.bmm(W.t().unsqueeze(0).expand(B, -1, -1), dy.transpose(1, 2)) if ctx.needs_input_grad[0] else None
-        dW = torch.bmm(dy.transpose(1, 2), y_pre.transpose(1, 2)).sum(0) if ctx.needs_input_grad[1] else None
-        db = dy.sum((0, 1)) if ctx.needs_input_grad[2] else None
+        B, C, L = y_pre.shape
+        Do = W.shape[0]
+        dy = dy.contiguous()
+        if ops.gemm_mode() == "torch":
+            d_pre = torch.bmm(W.t().unsqueeze(0).expand(B, -1, -1), dy.transpose(1, 2)) if ctx.needs_input_grad[0] else None
+            dW = torch.bmm(dy.transpose(1, 2), y_pre.transpose(1, 2)).sum(0) if ctx.needs_input_grad[1] else None
+            db = dy.sum((0, 1)) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+            return d_pre, dW, db
+        d_pre = dW = db = None
+        if ctx.needs_input_grad[0]:
+            d_pre = torch.empty_like(y_pre)
+            # dYpre^T (L x C, ld L) = dY (L x Do; stored (Do x L, ld Do) -> op T) W (Do x C; stored (C x Do, ld C) -> op T)
+            ops.gemm(1, 1, L, C, Do, dy, Do, L * Do, W, C, 0, d_pre, L, C * L, batch=B)
+        if ctx.needs_input_grad[1]:
+            dW = torch.empty_like(W)
+            # dW^T (C x Do, ld C) = sum_b Ypre_b (C x L; stored (L x C, ld L) -> op T) dY_b (L x Do; stored (Do x L) -> op T)
+            for b in range(B):
+                ops.gemm(1, 1, C, Do, L, y_pre[b], L, 0, dy[b], Do, 0, dW, C, 0, batch=1, beta=0.0 if b == 0 else 1.0)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum((0, 1))
         return d_pre, dW, db
 
 

@@ -36,7 +36,9 @@ def workspace(B, D, L, backward, device):
     if buf is None or buf.numel() < n:
         buf = torch.empty(n, dtype=torch.uint8, device=device)
         _ws_cache[key] = buf
-    return buf
+    # hand the library exactly the bytes this call asked for: the group size (rows in flight, sized to
+    # stay L2-resident) is derived from the workspace size
+    return buf[:n]
 
 
 def spectrum_elems(L):
@@ -211,3 +213,37 @@ def fftconv_backward(dout, u, kspec, Dvec):
         _lib.check(_lib.lib().hyena_b200_fftconv_bwd(_ptr(dout), _ptr(u), _ptr(kspec), _ptr(Dvec), _ptr(du), _ptr(dk),
                                                      _ptr(dD), B, H, L, _ptr(ws), ws.numel(), _stream()))
     return du, dk, dD
+
+
+# ------------------------------------------------------------------------------------------ projections
+_gemm_ws = {}
+_gemm_mode = None
+
+
+def gemm_mode():
+    """'bf16x9' when the CUDA 12.9 cuBLASLt with fp32 emulation is usable, else 'torch' (torch.bmm on the
+    bundled cuBLAS).  HYENA_B200_GEMM=torch forces the latter.  Both are GPU library GEMMs."""
+    global _gemm_mode
+    if _gemm_mode is None:
+        import os
+        want = os.environ.get("HYENA_B200_GEMM", "bf16x9")
+        _gemm_mode = "torch"
+        if want != "torch" and torch.cuda.is_available() and _lib.lib().hyena_b200_gemm_available():
+            _gemm_mode = "bf16x9"
+    return _gemm_mode
+
+
+def gemm(transa, transb, m, n, k, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, batch=1, beta=0.0, bias=None,
+         emulate=True):
+    """Column-major strided-batched C = op(A) op(B) + beta*C (+bias) on cuBLASLt 12.9 (see csrc/gemm.cu)."""
+    dev = C.device
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    ws = _gemm_ws.get(key)
+    if ws is None:
+        ws = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+        _gemm_ws[key] = ws
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().hyena_b200_gemm(int(transa), int(transb), m, n, k, 1.0, _ptr(A), lda, strideA,
+                                              _ptr(B), ldb, strideB, float(beta), _ptr(C), ldc, strideC, batch,
+                                              _ptr(bias), int(emulate), _ptr(ws), ws.numel(), _stream()))
+    return C

@@ -121,6 +121,17 @@ HY_API int hyena_b200_fftconv_bwd(const float* dout, const float* u, const float
                            float* du, float* dk, float* dD, int B, int H, int L,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- projections (library GEMM at the boundary of the custom-kernel span) ------------------------
+ * in_proj / out_proj (hyena.py:350-351, :391, :440) are plain GEMMs and stay cuBLASLt calls.  These two
+ * entry points run them on the CUDA 12.9 cuBLASLt with CUBLAS_COMPUTE_32F_EMULATED_16BFX9 (fp32 emulated
+ * on bf16 tensor cores, fp32-level accuracy).  Column-major, strided-batched:
+ * C[m,n] = alpha * op(A) op(B) + beta * C (+ bias[m]); op: 0 = N, 1 = T. */
+HY_API int hyena_b200_gemm_available(void);
+HY_API int hyena_b200_gemm(int transa, int transb, int m, int n, int k, float alpha, const float* A, int lda,
+                           long long strideA, const float* B, int ldb, long long strideB, float beta, float* C,
+                           int ldc, long long strideC, int batch, const float* bias, int emulate, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

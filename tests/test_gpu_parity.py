@@ -260,3 +260,33 @@ def test_state_dict_roundtrip_and_optim_attrs():
         assert tuple(v.shape) == tuple(G["sd"][k].shape), k
     assert op.filter_fn.implicit_filter[0].weight._optim == {"weight_decay": 0, "lr": 6e-4}
     assert H.registry.layer["hyena"] is H.HyenaOperator
+
+
+# ------------------------------------------------------------------------------------------ projections
+def test_projection_gemms_match_fp64():
+    """in/out projections through csrc/gemm.cu (cuBLASLt BF16x9 fp32 emulation) vs float64 matmuls."""
+    import hyena_dna_b200 as H
+    from importlib import import_module
+    hy = import_module("hyena_dna_b200.hyena")
+    dev = _dev()
+    g = torch.Generator().manual_seed(9)
+    B, L, D = 2, 4096, 64
+    u = torch.randn(B, L, D, generator=g).to(dev).requires_grad_(True)
+    W = (torch.randn(3 * D, D, generator=g) * 0.05).to(dev).requires_grad_(True)
+    p = hy._InProj.apply(u, W)
+    ref = torch.matmul(W.double(), u.double().transpose(1, 2))
+    _close(p, ref, f"in_proj ({H.ops.gemm_mode()})")
+    dp = torch.randn(B, 3 * D, L, generator=g).to(dev)
+    p.backward(dp)
+    _close(u.grad, torch.matmul(dp.double().transpose(1, 2), W.double()), "in_proj du")
+    _close(W.grad, torch.matmul(dp.double(), u.double()).sum(0), "in_proj dW", rtol=2e-3)
+    yp = torch.randn(B, D, L, generator=g).to(dev).requires_grad_(True)
+    Wo = (torch.randn(D, D, generator=g) * 0.05).to(dev).requires_grad_(True)
+    bo = torch.randn(D, generator=g).to(dev).requires_grad_(True)
+    y = hy._OutProj.apply(yp, Wo, bo)
+    _close(y, torch.matmul(yp.double().transpose(1, 2), Wo.double().t()) + bo.double(), "out_proj")
+    dy = torch.randn(B, L, D, generator=g).to(dev)
+    y.backward(dy)
+    _close(yp.grad, torch.matmul(Wo.double().t(), dy.double().transpose(1, 2)), "out_proj dy_pre")
+    _close(Wo.grad, torch.matmul(dy.double().transpose(1, 2), yp.double().transpose(1, 2)).sum(0), "out_proj dW", rtol=2e-3)
+    _close(bo.grad, dy.double().sum((0, 1)), "out_proj db", rtol=2e-3)
