@@ -94,12 +94,12 @@ static int get_twiddles(cudaStream_t s, Twiddles* out) {
 }
 
 // ---------------------------------------------------------------- geometry
-static int log_m1_for(int L) {        // M = 1024 * 2^logM1 >= L
-  int lg = 0;
-  while (((size_t)kM2 << lg) < (size_t)L) ++lg;
+static int log_m_for(int L) {         // M = 2^logM >= max(L, 1024)
+  int lg = 10;
+  while (((size_t)1 << lg) < (size_t)L) ++lg;
   return lg;
 }
-static size_t row_bytes(int L) { return ((size_t)kM2 << log_m1_for(L)) * sizeof(float2); }
+static size_t row_bytes(int L) { return ((size_t)1 << log_m_for(L)) * sizeof(float2); }
 
 static size_t group_budget_bytes() {
   // scratch rows in flight per launch group.  Measured on B200 (profiles/r1_group_sweep.txt): the passes are
@@ -156,8 +156,9 @@ static int check_shape(int B, int D, int L) {
 static PassArgs base_args(int B, int D, int L, const Twiddles& T) {
   PassArgs a;
   memset(&a, 0, sizeof(a));
-  a.L = L; a.logM1 = log_m1_for(L); a.B = B; a.D = D; a.T = T;
-  a.scale = 1.0f / (4.0f * (float)((size_t)kM2 << a.logM1));
+  const int logM = log_m_for(L);
+  a.L = L; a.logM2 = log_m2_for(logM); a.logM1 = logM - a.logM2; a.B = B; a.D = D; a.T = T;
+  a.scale = 1.0f / (4.0f * (float)((size_t)1 << logM));
   return a;
 }
 
@@ -206,7 +207,7 @@ HY_API const char* hyena_b200_kind_name(int kind) {
   return (kind >= 0 && kind < K_COUNT) ? names[kind] : "?";
 }
 
-HY_API size_t hyena_b200_spectrum_elems(int L) { return L < 1 ? 0 : ((size_t)kM2 << log_m1_for(L)); }
+HY_API size_t hyena_b200_spectrum_elems(int L) { return L < 1 ? 0 : ((size_t)1 << log_m_for(L)); }
 
 HY_API size_t hyena_b200_workspace_min_bytes(int B, int D, int L, int backward) {
   (void)D;

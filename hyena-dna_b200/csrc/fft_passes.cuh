@@ -1,7 +1,9 @@
 // The three passes of the long real-FFT convolution (see DESIGN.md "Kernels").
 //
 // A (batch, channel) row of L real samples is packed as z[m] = x[2m] + i x[2m+1] and zero padded
-// to M = M1 * 1024 complex points (n = 2M >= 2L).  M is split as m = 1024*m1 + m2, k = k1 + M1*k2:
+// to M = M1 * M2 complex points (n = 2M >= 2L).  M is split as m = M2*m1 + m2, k = k1 + M1*k2, with
+// the row length M2 = 1024 for M <= 2^16 and M2 = 4096 above (so that a column tile of the large
+// transforms spans 256 contiguous bytes of every row it touches):
 //
 //   pass 1  col_fwd : for every column m2, FFT over m1 (length M1) and twiddle W_M^{m2 k1}
 //                     -> scratch A[row][k1][m2]                      (input side fused in)
@@ -17,8 +19,8 @@
 
 namespace hy {
 
-constexpr int kM2 = 1024;       // row FFT length (fixed)
-constexpr int kLogM2 = 10;
+// row FFT length M2 = 2^logM2: 1024 (one warp per row) or 4096 (four warps per row)
+__host__ __device__ constexpr int log_m2_for(int logM) { return logM >= 17 ? 12 : 10; }
 
 // ------------------------------------------------------------------------------------------------
 // short depthwise filter + gates (reference: src/models/sequence/hyena.py:363-369, :394, :420, :432)
@@ -87,7 +89,8 @@ enum RowMode { ROW_FILTER = 0, ROW_CONV_FWD = 1, ROW_CONV_BWD = 2 };
 // Rows of one launch are numbered r = ci*B + b (all batches of a channel adjacent), channel c = c0 + ci.
 struct PassArgs {
   int L;            // samples per row
-  int logM1;        // M = 2^logM1 * 1024
+  int logM1;        // M = 2^logM1 * 2^logM2
+  int logM2;        // 10 or 12
   int B;            // batch
   int D;            // channels (d_model, or H for the plain fftconv API)
   int c0;           // first channel of this launch
@@ -117,18 +120,20 @@ __device__ __forceinline__ size_t row_off(int b, int ch, int nch, int L) { retur
 // ------------------------------------------------------------------------------------------------
 // column-pass geometry
 // ------------------------------------------------------------------------------------------------
-template <int LOGM1>
+template <int LOGM1, int LOGM2>
 struct ColGeo {
   static constexpr int M1 = 1 << LOGM1;
+  static constexpr int M2 = 1 << LOGM2;
   static constexpr bool TWO = LOGM1 >= 5;                       // thread-group FFT (>= 32 points)
   static constexpr int R2 = TWO ? M1 / 32 : 1;
   static constexpr int G = TWO ? 1 : 32 / M1;                   // columns per thread when M1 < 32
   static constexpr int THREADS = TWO ? 256 : (32 * M1 < 256 ? 32 * M1 : 256);
   static constexpr int C = TWO ? 256 / R2 : THREADS * G;        // columns per CTA
-  static constexpr int CTAS = kM2 / C;                          // CTAs per row
+  static constexpr int CTAS = M2 / C;                           // CTAs per row
   static constexpr int PAD = C >= 16 ? 1 : 16 / C;
   static constexpr int PITCH = TWO ? Geo<TWO ? LOGM1 : 5>::ex_elems() + PAD : 0;   // exchange elems per column
   static constexpr size_t SMEM = (R2 > 1) ? (size_t)C * PITCH * sizeof(float2) : 0;
+  static_assert(C <= M2, "column tile wider than a row");
 };
 
 struct CtaSync { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
@@ -157,11 +162,12 @@ __device__ __forceinline__ float2 col_input(const PassArgs& a, int b, int c, int
 // pass 1: forward column FFT with the input side fused in
 // grid (CTAS, rows); block ColGeo::THREADS
 // ------------------------------------------------------------------------------------------------
-template <int LOGM1, int MODE>
-__global__ void __launch_bounds__(ColGeo<LOGM1>::THREADS, ColGeo<LOGM1>::TWO ? 2 : 1)
+template <int LOGM1, int LOGM2, int MODE>
+__global__ void __launch_bounds__(ColGeo<LOGM1, LOGM2>::THREADS, ColGeo<LOGM1, LOGM2>::TWO ? 2 : 1)
 col_fwd_kernel(const PassArgs a) {
-  using CG = ColGeo<LOGM1>;
+  using CG = ColGeo<LOGM1, LOGM2>;
   constexpr int M1 = CG::M1;
+  constexpr int kM2 = CG::M2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* smem = reinterpret_cast<float2*>(smem_raw);
 
@@ -170,7 +176,7 @@ col_fwd_kernel(const PassArgs a) {
   const int colbase = blockIdx.x * CG::C;
   const int L = a.L;
   const bool vec = a.vec != 0;
-  const int logM = LOGM1 + kLogM2;
+  constexpr int logM = LOGM1 + LOGM2;
   float2* Arow = a.A + (size_t)r * ((size_t)M1 * kM2);
 
   Taps ka{}, kb{};
@@ -308,11 +314,12 @@ __device__ __forceinline__ void inv_output(const PassArgs& a, InvCtx& cx, int b,
   inv_finish<MODE>(a, cx, b, c, t0, vec, y, in);
 }
 
-template <int LOGM1, int MODE>
-__global__ void __launch_bounds__(ColGeo<LOGM1>::THREADS, ColGeo<LOGM1>::TWO ? 2 : 1)
+template <int LOGM1, int LOGM2, int MODE>
+__global__ void __launch_bounds__(ColGeo<LOGM1, LOGM2>::THREADS, ColGeo<LOGM1, LOGM2>::TWO ? 2 : 1)
 col_inv_kernel(const PassArgs a) {
-  using CG = ColGeo<LOGM1>;
+  using CG = ColGeo<LOGM1, LOGM2>;
   constexpr int M1 = CG::M1;
+  constexpr int kM2 = CG::M2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* smem = reinterpret_cast<float2*>(smem_raw);
   __shared__ float red_smem[8];
@@ -398,68 +405,100 @@ col_inv_kernel(const PassArgs a) {
 
 // ------------------------------------------------------------------------------------------------
 // pass 2: row FFTs + pointwise spectrum product + inverse row FFTs
-// One warp per k1 row; warps 2i / 2i+1 of a CTA hold the two rows of a (k, M-k) pair.
-// grid (max(1, M1/8), channel-rows); block 32 * min(8, M1)
+// A row of M2 = 2^LOGM2 points is owned by TPR = M2/32 threads (one warp for 1024, four for 4096);
+// a CTA of 256 threads holds 256/TPR rows, arranged so that both rows of a (k, M-k) pair sit in the
+// same CTA.  grid (pairs / pairs-per-CTA, channel-rows)
 // ------------------------------------------------------------------------------------------------
-constexpr int kRowEx = 32 * 33;                       // exchange elems of one 1024-point transform
-constexpr int kRowPitch = kRowEx;
+template <int LOGM2>
+struct RowGeo {
+  static constexpr int M2 = 1 << LOGM2;
+  static constexpr int TPR = M2 / 32;                         // threads per row
+  static constexpr int ROWS = 256 / TPR;                      // rows per full CTA (8 or 2)
+  static constexpr int EX = LOGM2 == 10 ? 32 * 33 : kEx4096;  // exchange elems per row (>= M2: also holds a spectrum)
+  static_assert(EX >= M2, "the exchange area doubles as a natural-order row buffer");
+};
 
 struct RowIds {
-  int k1;        // this warp's row
+  int k1;        // this row
   int pk1;       // row holding the partner bins
-  int pwarp;     // warp of this CTA that holds row pk1
+  int pslot;     // row slot of this CTA that holds row pk1
   int nz;        // 1 if k1 != 0 (partner column is M2-1-k2 instead of (M2-k2)%M2)
 };
 
-__device__ __forceinline__ RowIds row_ids(int M1, int cta, int warp) {
+__device__ __forceinline__ RowIds row_ids(int M1, int rows_per_cta, int cta, int slot) {
   RowIds id;
-  if (M1 == 1) { id.k1 = 0; id.pk1 = 0; id.pwarp = 0; id.nz = 0; return id; }
-  const int pair = cta * 4 + (warp >> 1);        // pair 0 = rows (0, M1/2), both self-paired
-  const int second = warp & 1;
+  if (M1 == 1) { id.k1 = 0; id.pk1 = 0; id.pslot = 0; id.nz = 0; return id; }
+  const int pair = cta * (rows_per_cta / 2) + (slot >> 1);      // pair 0 = rows (0, M1/2), both self-paired
+  const int second = slot & 1;
   if (pair == 0) {
     id.k1 = second ? M1 / 2 : 0;
-    id.pk1 = id.k1; id.pwarp = warp;
+    id.pk1 = id.k1; id.pslot = slot;
   } else {
     id.k1 = second ? M1 - pair : pair;
-    id.pk1 = M1 - id.k1; id.pwarp = warp ^ 1;
+    id.pk1 = M1 - id.k1; id.pslot = slot ^ 1;
   }
   id.nz = id.k1 != 0;
   return id;
 }
 
-// 1024-point forward FFT of row `src` by one warp; natural bin k2 = 32*s + lane left in dst[k2] (shared).
-__device__ __forceinline__ void row_fft_to_smem(const float2* __restrict__ src, float2* ex, float2* dst, int lane,
-                                                const float2* tw1024) {
+// barrier over the TPR threads of one row
+template <int LOGM2>
+struct RowSync {
+  int id;
+  __device__ __forceinline__ void operator()() const {
+    if constexpr (LOGM2 == 10) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(RowGeo<LOGM2>::TPR) : "memory");
+  }
+};
+
+template <int LOGM2, bool INV>
+__device__ __forceinline__ void row_fft(float2 (&v)[32], float2* ex, int q, const Twiddles& T, RowSync<LOGM2> sync) {
+  if constexpr (LOGM2 == 10) block_fft<10, INV, false>(v, ex, q, T.tw1024, sync);
+  else block_fft4096<INV>(v, ex, q, T, sync);
+}
+template <int LOGM2>
+struct RowSlot {
+  __host__ __device__ static constexpr int at(int s) { return LOGM2 == 10 ? Geo<10>::slot(s) : Slot4096::at(s); }
+};
+
+// forward FFT of one row; natural bin k2 = TPR*s + q left in dst[k2] (dst may be `ex` itself)
+template <int LOGM2>
+__device__ __forceinline__ void row_fft_to_smem(const float2* __restrict__ src, float2* ex, float2* dst, int q,
+                                                const Twiddles& T, RowSync<LOGM2> sync) {
+  constexpr int TPR = RowGeo<LOGM2>::TPR;
   float2 v[32];
   static_for<0, 32>([&](auto n_) {
     constexpr int n1 = decltype(n_)::value;
-    v[n1] = src[32 * n1 + lane];
+    v[n1] = src[TPR * n1 + q];
   });
-  block_fft<10, false, false>(v, ex, lane, tw1024, WarpSync{});
+  row_fft<LOGM2, false>(v, ex, q, T, sync);
+  if (dst == ex) sync();                               // all reads of the exchange area are done
   static_for<0, 32>([&](auto s_) {
     constexpr int s = decltype(s_)::value;
-    dst[32 * s + lane] = v[Geo<10>::slot(s)];
+    dst[TPR * s + q] = v[RowSlot<LOGM2>::at(s)];
   });
 }
 
-// inverse 1024-point FFT of v (natural slots), conj 4-step twiddle, store to dst[m2 = 32*s + lane]
-__device__ __forceinline__ void row_ifft_store(float2 (&v)[32], float2* ex, float2* __restrict__ dst, int lane, int k1,
-                                               int logM, const Twiddles& T) {
-  block_fft<10, true, false>(v, ex, lane, T.tw1024, WarpSync{});
+// inverse FFT of v (natural slots), conj 4-step twiddle W_M^{-k1 m2}, store to dst[m2 = TPR*s + q]
+template <int LOGM2>
+__device__ __forceinline__ void row_ifft_store(float2 (&v)[32], float2* ex, float2* __restrict__ dst, int q, int k1,
+                                               int logM, const Twiddles& T, RowSync<LOGM2> sync) {
+  constexpr int TPR = RowGeo<LOGM2>::TPR;
+  row_fft<LOGM2, true>(v, ex, q, T, sync);
   const int sh = 20 - logM;
   const uint32_t Mmask = (1u << logM) - 1u;
-  const uint32_t eb = ((uint32_t)k1 * (uint32_t)lane) & Mmask;
-  const uint32_t es = ((uint32_t)k1 * 32u) & Mmask;
+  const uint32_t eb = ((uint32_t)k1 * (uint32_t)q) & Mmask;
+  const uint32_t es = ((uint32_t)k1 * (uint32_t)TPR) & Mmask;
   float2 base = root20(T, eb << sh);
   float2 s1 = root20(T, (es & Mmask) << sh);
   float2 s2 = root20(T, ((2u * es) & Mmask) << sh);
   float2 s4 = root20(T, ((4u * es) & Mmask) << sh);
   float2 s8 = root20(T, ((8u * es) & Mmask) << sh);
   float2 s16 = root20(T, ((16u * es) & Mmask) << sh);
-  mul_geometric<true>(v, base, s1, s2, s4, s8, s16, SlotIdx<10>{});
+  mul_geometric<true>(v, base, s1, s2, s4, s8, s16, RowSlot<LOGM2>{});
   static_for<0, 32>([&](auto s_) {
     constexpr int s = decltype(s_)::value;
-    dst[32 * s + lane] = v[Geo<10>::slot(s)];
+    dst[TPR * s + q] = v[RowSlot<LOGM2>::at(s)];
   });
 }
 
@@ -469,91 +508,95 @@ __device__ __forceinline__ void even_odd(float2 z, float2 pc, float2& e, float2&
   o = cmul_negi(csub(z, pc));
 }
 
-template <int MODE>
+// shared memory per CTA (complex elements): FILTER: rows*EX; CONV_FWD: rows*EX (spectrum aliased onto the
+// exchange area); CONV_BWD: rows*(EX + M2) (dc spectrum separate, g spectrum aliased onto the exchange area)
+template <int MODE, int LOGM2>
+__host__ __device__ constexpr size_t row_smem_elems(int rows) {
+  return (size_t)rows * (RowGeo<LOGM2>::EX + (MODE == ROW_CONV_BWD ? RowGeo<LOGM2>::M2 : 0));
+}
+
+template <int MODE, int LOGM2>
 __global__ void __launch_bounds__(256, MODE == ROW_CONV_BWD ? 1 : 2)
 row_pass_kernel(const PassArgs a) {
+  using RG = RowGeo<LOGM2>;
+  constexpr int M2 = RG::M2, TPR = RG::TPR;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* smem = reinterpret_cast<float2*>(smem_raw);
   const int M1 = 1 << a.logM1;
-  const int logM = a.logM1 + kLogM2;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nwarps = blockDim.x >> 5;
-  const RowIds id = row_ids(M1, blockIdx.x, warp);
-  const size_t rowElems = (size_t)M1 * kM2;
+  const int logM = a.logM1 + LOGM2;
+  const int slot = threadIdx.x / TPR, q = threadIdx.x % TPR;
+  const int nslots = blockDim.x / TPR;
+  const RowIds id = row_ids(M1, nslots, blockIdx.x, slot);
+  const size_t rowElems = (size_t)M1 * M2;
+  const RowSync<LOGM2> rsync{1 + slot};
 
-  // shared memory carve-up: per-warp exchange, then per-warp natural-order spectrum buffers
-  float2* ex = smem + warp * kRowPitch;
-  float2* zbuf = smem + nwarps * kRowPitch;            // [warp][1024]   (ROW_CONV_*)
-  float2* gbuf = zbuf + nwarps * kM2;                  // [warp][1024]   (ROW_CONV_BWD)
+  float2* ex = smem + slot * RG::EX;                    // exchange area, doubles as a spectrum buffer
+  float2* exp_ = smem + id.pslot * RG::EX;              // the partner row's
+  float2* zbuf = smem + nslots * RG::EX + slot * M2;    // ROW_CONV_BWD only: dc spectrum
+  float2* zbufp = smem + nslots * RG::EX + id.pslot * M2;
 
   if constexpr (MODE == ROW_FILTER) {
     const int c = a.c0 + blockIdx.y;
-    const float2* src = a.A + (size_t)blockIdx.y * rowElems + (size_t)id.k1 * kM2;
-    float2* dst = a.kspec_out + (size_t)c * rowElems + (size_t)id.k1 * kM2;
+    const float2* src = a.A + (size_t)blockIdx.y * rowElems + (size_t)id.k1 * M2;
+    float2* dst = a.kspec_out + (size_t)c * rowElems + (size_t)id.k1 * M2;
     float2 v[32];
-    static_for<0, 32>([&](auto n_) { constexpr int n1 = decltype(n_)::value; v[n1] = src[32 * n1 + lane]; });
-    block_fft<10, false, false>(v, ex, lane, a.T.tw1024, WarpSync{});
+    static_for<0, 32>([&](auto n_) { constexpr int n1 = decltype(n_)::value; v[n1] = src[TPR * n1 + q]; });
+    row_fft<LOGM2, false>(v, ex, q, a.T, rsync);
     static_for<0, 32>([&](auto s_) {
       constexpr int s = decltype(s_)::value;
-      dst[32 * s + lane] = v[Geo<10>::slot(s)];
+      dst[TPR * s + q] = v[RowSlot<LOGM2>::at(s)];
     });
     return;
   } else {
-    // W_M^k for k = k1 + M1*(32 s + lane) = base * W_32^s,  base = W_M^{k1} * W_1024^{lane}
-    const float2 wbase = cmul(root20(a.T, (uint32_t)id.k1 << (20 - logM)), __ldg(a.T.tw1024 + lane));
+    // W_M^k for k = k1 + M1*(TPR s + q) = base * W_32^s,  base = W_M^{k1} * W_{M2}^{q}
+    const float2 wbase = cmul(root20(a.T, (uint32_t)id.k1 << (20 - logM)), root20(a.T, (uint32_t)q << (20 - LOGM2)));
 
     if constexpr (MODE == ROW_CONV_FWD) {
       const int r = blockIdx.y;
       const int ci = r / a.B, c = a.c0 + ci;
-      float2* Arow = a.A + (size_t)r * rowElems + (size_t)id.k1 * kM2;
-      const float2* Krow = a.kspec + (size_t)c * rowElems + (size_t)id.k1 * kM2;
-      const float2* Kprow = a.kspec + (size_t)c * rowElems + (size_t)id.pk1 * kM2;
-      row_fft_to_smem(Arow, ex, zbuf + warp * kM2, lane, a.T.tw1024);
+      float2* Arow = a.A + (size_t)r * rowElems + (size_t)id.k1 * M2;
+      const float2* Krow = a.kspec + (size_t)c * rowElems + (size_t)id.k1 * M2;
+      const float2* Kprow = a.kspec + (size_t)c * rowElems + (size_t)id.pk1 * M2;
+      row_fft_to_smem<LOGM2>(Arow, ex, ex, q, a.T, rsync);
       __syncthreads();
-      const float2* zme = zbuf + warp * kM2;
-      const float2* zpa = zbuf + id.pwarp * kM2;
       float2 v[32];
       static_for<0, 32>([&](auto s_) {
         constexpr int s = decltype(s_)::value;
-        const int k2 = 32 * s + lane;
-        const int pc = (kM2 - k2 - id.nz) & (kM2 - 1);
+        const int k2 = TPR * s + q;
+        const int pc = (M2 - k2 - id.nz) & (M2 - 1);
         float2 E, O, He, Ho;
-        even_odd(zme[k2], cconj(zpa[pc]), E, O);
+        even_odd(ex[k2], cconj(exp_[pc]), E, O);
         even_odd(__ldg(Krow + k2), cconj(__ldg(Kprow + pc)), He, Ho);
         const float2 W = mul_w32<s, false>(wbase);
         float2 Ye = cadd(cmul(E, He), cmul(W, cmul(O, Ho)));
         float2 Yo = cadd(cmul(E, Ho), cmul(O, He));
         v[s] = cadd(Ye, cmul_i(Yo));
       });
-      row_ifft_store(v, ex, Arow, lane, id.k1, logM, a.T);
+      __syncthreads();                                  // partner rows are done reading this row's spectrum
+      row_ifft_store<LOGM2>(v, ex, Arow, q, id.k1, logM, a.T, rsync);
     } else {   // ROW_CONV_BWD: loop over the batch, accumulate dK' in registers
       const int ci = blockIdx.y, c = a.c0 + ci;
-      const float2* Krow = a.kspec + (size_t)c * rowElems + (size_t)id.k1 * kM2;
-      const float2* Kprow = a.kspec + (size_t)c * rowElems + (size_t)id.pk1 * kM2;
+      const float2* Krow = a.kspec + (size_t)c * rowElems + (size_t)id.k1 * M2;
+      const float2* Kprow = a.kspec + (size_t)c * rowElems + (size_t)id.pk1 * M2;
       float2 acc[32];
       static_for<0, 32>([&](auto s_) { acc[decltype(s_)::value] = make_float2(0.f, 0.f); });
       for (int b = 0; b < a.B; ++b) {
         const size_t r = (size_t)ci * a.B + b;
-        float2* Drow = a.A + r * rowElems + (size_t)id.k1 * kM2;
-        const float2* Grow = a.A2 + r * rowElems + (size_t)id.k1 * kM2;
-        if (b > 0) __syncthreads();                   // previous iteration's readers of zbuf/gbuf are done
-        row_fft_to_smem(Drow, ex, zbuf + warp * kM2, lane, a.T.tw1024);
-        __syncwarp();
-        row_fft_to_smem(Grow, ex, gbuf + warp * kM2, lane, a.T.tw1024);
+        float2* Drow = a.A + r * rowElems + (size_t)id.k1 * M2;
+        const float2* Grow = a.A2 + r * rowElems + (size_t)id.k1 * M2;
+        row_fft_to_smem<LOGM2>(Drow, ex, zbuf, q, a.T, rsync);     // dc spectrum -> zbuf
+        rsync();
+        row_fft_to_smem<LOGM2>(Grow, ex, ex, q, a.T, rsync);       // g spectrum  -> the exchange area itself
         __syncthreads();
-        const float2* zme = zbuf + warp * kM2;
-        const float2* zpa = zbuf + id.pwarp * kM2;
-        const float2* gme = gbuf + warp * kM2;
-        const float2* gpa = gbuf + id.pwarp * kM2;
         float2 v[32];
         static_for<0, 32>([&](auto s_) {
           constexpr int s = decltype(s_)::value;
-          const int k2 = 32 * s + lane;
-          const int pc = (kM2 - k2 - id.nz) & (kM2 - 1);
+          const int k2 = TPR * s + q;
+          const int pc = (M2 - k2 - id.nz) & (M2 - 1);
           float2 E, O, He, Ho, Ge, Go;
-          even_odd(zme[k2], cconj(zpa[pc]), E, O);
+          even_odd(zbuf[k2], cconj(zbufp[pc]), E, O);
           even_odd(__ldg(Krow + k2), cconj(__ldg(Kprow + pc)), He, Ho);
-          even_odd(gme[k2], cconj(gpa[pc]), Ge, Go);
+          even_odd(ex[k2], cconj(exp_[pc]), Ge, Go);
           const float2 W = mul_w32<s, false>(wbase);
           const float2 WE = cmulc(E, W);                                  // conj(W) * E
           // dg spectrum: corr(dc, k)
@@ -565,11 +608,12 @@ row_pass_kernel(const PassArgs a) {
           float2 Ko = cadd(cmulc(WE, Go), cmulc(O, Ge));
           acc[s] = cadd(acc[s], cadd(Ke, cmul_i(Ko)));
         });
-        row_ifft_store(v, ex, Drow, lane, id.k1, logM, a.T);
+        __syncthreads();                                // spectra consumed: the exchange area may be reused
+        row_ifft_store<LOGM2>(v, ex, Drow, q, id.k1, logM, a.T, rsync);
+        rsync();
       }
-      float2* Krow_out = a.A3 + (size_t)ci * rowElems + (size_t)id.k1 * kM2;
-      __syncwarp();                                   // the exchange area is reused right away
-      row_ifft_store(acc, ex, Krow_out, lane, id.k1, logM, a.T);
+      float2* Krow_out = a.A3 + (size_t)ci * rowElems + (size_t)id.k1 * M2;
+      row_ifft_store<LOGM2>(acc, ex, Krow_out, q, id.k1, logM, a.T, rsync);
     }
   }
 }

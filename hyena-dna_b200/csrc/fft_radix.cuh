@@ -164,4 +164,60 @@ __device__ __forceinline__ void block_fft(float2 (&v)[32], float2* ex, int q, co
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// 4096-point FFT spread over 128 threads (32 points each): 4096 = 32 x (32 x 4), two exchanges.
+//   in : natural slot s (element 128*s + q) in v[s], q = thread index in [0,128)
+//   out: natural slot s in v[Slot4096::at(s)]
+//   ex : 32*129 complex of shared memory private to this transform; `sync` is a barrier over the
+//        128 threads of the transform.
+struct Slot4096 { __host__ __device__ static constexpr int at(int s) { return 4 * (s % 8) + brev(s / 8, 2); } };
+constexpr int kEx4096 = 32 * 129;
+
+template <bool INV, class SYNC>
+__device__ __forceinline__ void block_fft4096(float2 (&v)[32], float2* ex, int q, const Twiddles& T, SYNC sync) {
+  // stage 1: radix-32 over n1 (stride 128); X1[k1'] in v[brev5(k1')]; twiddle W_4096^{q k1'}
+  dif<32, 0, INV, 32>(v);
+  {
+    const uint32_t e = (uint32_t)q;             // exponents modulo 4096, scaled by 2^8 into the 2^20 tables
+    float2 s1 = root20(T, (e & 4095u) << 8), s2 = root20(T, ((2u * e) & 4095u) << 8),
+           s4 = root20(T, ((4u * e) & 4095u) << 8), s8 = root20(T, ((8u * e) & 4095u) << 8),
+           s16 = root20(T, ((16u * e) & 4095u) << 8);
+    mul_geometric<INV>(v, make_float2(1.f, 0.f), s1, s2, s4, s8, s16, Brev5Idx{});
+  }
+  static_for<0, 32>([&](auto k_) {
+    constexpr int k1 = decltype(k_)::value;
+    ex[k1 * 129 + q] = v[brev(k1, 5)];
+  });
+  sync();
+  // stage 2a: thread (k1' = q & 31, n2'' = q >> 5): radix-32 over n1'' of y[4 n1'' + n2'']; twiddle W_128^{n2'' k1''}
+  const int k1p = q & 31, c = q >> 5;
+  static_for<0, 32>([&](auto n_) {
+    constexpr int n1 = decltype(n_)::value;
+    v[n1] = ex[k1p * 129 + 4 * n1 + c];
+  });
+  sync();                                        // everyone has read before the area is reused
+  dif<32, 0, INV, 32>(v);
+  {
+    const uint32_t e = (uint32_t)c * 8u;        // W_128^c = W_1024^{8c}
+    float2 s1 = __ldg(T.tw1024 + (e & 1023u)), s2 = __ldg(T.tw1024 + ((2u * e) & 1023u)),
+           s4 = __ldg(T.tw1024 + ((4u * e) & 1023u)), s8 = __ldg(T.tw1024 + ((8u * e) & 1023u)),
+           s16 = __ldg(T.tw1024 + ((16u * e) & 1023u));
+    mul_geometric<INV>(v, make_float2(1.f, 0.f), s1, s2, s4, s8, s16, Brev5Idx{});
+  }
+  static_for<0, 32>([&](auto k_) {
+    constexpr int k1 = decltype(k_)::value;
+    ex[k1p * 129 + 4 * k1 + c] = v[brev(k1, 5)];
+  });
+  sync();
+  // stage 2b: thread q owns (k1', k1'' = c + 4j), j < 8: radix-4 over n2''
+  static_for<0, 8>([&](auto j_) {
+    constexpr int j = decltype(j_)::value;
+    static_for<0, 4>([&](auto n_) {
+      constexpr int n = decltype(n_)::value;
+      v[4 * j + n] = ex[k1p * 129 + (c + 4 * j) * 4 + n];
+    });
+  });
+  static_for<0, 8>([&](auto j_) { dif<4, 4 * decltype(j_)::value, INV, 32>(v); });
+}
+
 }  // namespace hy

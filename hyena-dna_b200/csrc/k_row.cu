@@ -1,29 +1,34 @@
 #include "launch.h"
 namespace hy {
 
-template <int MODE>
+template <int MODE, int LOGM2>
 static cudaError_t go(const PassArgs& a, int rows, cudaStream_t s) {
+  using RG = RowGeo<LOGM2>;
   const int M1 = 1 << a.logM1;
-  const int nwarps = M1 < 8 ? M1 : 8;
-  const int ctas = M1 < 8 ? 1 : M1 / 8;
-  size_t elems = (size_t)nwarps * kRowPitch;
-  if (MODE == ROW_CONV_FWD) elems += (size_t)nwarps * kM2;
-  if (MODE == ROW_CONV_BWD) elems += (size_t)nwarps * 2 * kM2;
-  const size_t smem = elems * sizeof(float2);
-  auto kern = row_pass_kernel<MODE>;
+  const int nslots = M1 < RG::ROWS ? M1 : RG::ROWS;
+  const int ctas = M1 < RG::ROWS ? 1 : M1 / RG::ROWS;
+  const size_t smem = row_smem_elems<MODE, LOGM2>(nslots) * sizeof(float2);
+  auto kern = row_pass_kernel<MODE, LOGM2>;
   cudaError_t e = set_smem(kern, smem);
   if (e != cudaSuccess) return e;
   prof_begin(K_ROW + MODE, s);
-  kern<<<dim3(ctas, rows), nwarps * 32, smem, s>>>(a);
+  kern<<<dim3(ctas, rows), nslots * RG::TPR, smem, s>>>(a);
   prof_end(K_ROW + MODE, s);
   return cudaGetLastError();
 }
 
+template <int MODE>
+static cudaError_t by_len(const PassArgs& a, int rows, cudaStream_t s) {
+  if (a.logM2 == 10) return go<MODE, 10>(a, rows, s);
+  if (a.logM2 == 12) return go<MODE, 12>(a, rows, s);
+  return cudaErrorInvalidValue;
+}
+
 cudaError_t launch_row_pass(int mode, const PassArgs& a, int rows, cudaStream_t s) {
   switch (mode) {
-    case ROW_FILTER: return go<ROW_FILTER>(a, rows, s);
-    case ROW_CONV_FWD: return go<ROW_CONV_FWD>(a, rows, s);
-    case ROW_CONV_BWD: return go<ROW_CONV_BWD>(a, rows, s);
+    case ROW_FILTER: return by_len<ROW_FILTER>(a, rows, s);
+    case ROW_CONV_FWD: return by_len<ROW_CONV_FWD>(a, rows, s);
+    case ROW_CONV_BWD: return by_len<ROW_CONV_BWD>(a, rows, s);
   }
   return cudaErrorInvalidValue;
 }
