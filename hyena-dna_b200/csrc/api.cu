@@ -99,6 +99,13 @@ static int log_m_for(int L) {         // M = 2^logM >= max(L, 1024)
   while (((size_t)1 << lg) < (size_t)L) ++lg;
   return lg;
 }
+// row length: 4096 for M >= 2^17 unless HYENA_B200_LOGM2=10 asks for 1024-point rows everywhere
+static int pick_log_m2(int logM) {
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("HYENA_B200_LOGM2"); forced = e ? atoi(e) : 0; }
+  if (forced == 10) return 10;
+  return log_m2_for(logM);
+}
 static size_t row_bytes(int L) { return ((size_t)1 << log_m_for(L)) * sizeof(float2); }
 
 static size_t group_budget_bytes() {
@@ -125,6 +132,7 @@ static int channels_per_group(size_t bytes_for_A, int B, int D, int L) {
 }
 
 static bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 struct Carve { float2* A; float2* A2; float2* A3; int nch; };
 
@@ -157,7 +165,7 @@ static PassArgs base_args(int B, int D, int L, const Twiddles& T) {
   PassArgs a;
   memset(&a, 0, sizeof(a));
   const int logM = log_m_for(L);
-  a.L = L; a.logM2 = log_m2_for(logM); a.logM1 = logM - a.logM2; a.B = B; a.D = D; a.T = T;
+  a.L = L; a.logM2 = pick_log_m2(logM); a.logM1 = logM - a.logM2; a.B = B; a.D = D; a.T = T;
   a.scale = 1.0f / (4.0f * (float)((size_t)1 << logM));
   return a;
 }
@@ -298,6 +306,7 @@ HY_API int hyena_b200_core_fwd(const float* p, const float* in_bias, const float
   a.A = c.A; a.kspec = reinterpret_cast<const float2*>(kspec);
   a.p = p; a.in_bias = in_bias; a.sw = sw; a.sb = sb; a.fbias = fbias; a.out = y_pre; a.out2 = c_save;
   a.vec = ((L & 1) == 0) && aligned8(p) && aligned8(y_pre) && (!c_save || aligned8(c_save));
+  a.stage = ((L & 3) == 0) && aligned16(p) && !getenv("HYENA_B200_NO_STAGE");
   for (int c0 = 0; c0 < D; c0 += c.nch) {
     const int n = (D - c0 < c.nch) ? D - c0 : c.nch;
     a.c0 = c0;
@@ -325,6 +334,7 @@ HY_API int hyena_b200_core_bwd(const float* dy_pre, const float* p, const float*
   a.p = p; a.in_bias = in_bias; a.sw = sw; a.sb = sb; a.fbias = fbias;
   a.vec = ((L & 1) == 0) && aligned8(p) && aligned8(dy_pre) && aligned8(c_saved) && aligned8(dk) &&
           aligned8(ds_scratch) && aligned8(dp);
+  a.stage = ((L & 3) == 0) && aligned16(p) && aligned16(dy_pre) && aligned16(c_saved) && !getenv("HYENA_B200_NO_STAGE");
   for (int c0 = 0; c0 < D; c0 += c.nch) {
     const int n = (D - c0 < c.nch) ? D - c0 : c.nch;
     a.c0 = c0; a.B = B;

@@ -79,6 +79,60 @@ __device__ __forceinline__ void store_pair(float* __restrict__ row, int t0, int 
   if (t0 + 1 < L) row[t0 + 1] = v.y;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// cp.async staging of the HBM operands of a column tile.  A thread's 32-point transform needs 16 row
+// chunks of up to five tensors; pulling them through registers serialises the loads into batches
+// (register pressure), so they are copied global -> shared with cp.async (no registers, everything in
+// flight at once, 272-byte contiguous pieces per row) and the math then reads shared memory.
+// Requires L % 4 == 0 and 16-byte aligned rows (PassArgs.stage); otherwise the register path is used.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 16 : 0;                      // src-size 0: the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// rows [row0, row0+nrows) x columns [colbase, colbase+C) of the packed row `prow` (L floats), with a 4-float
+// halo on the left (the 3-tap filter reaches back two samples).  dst pitch: 2C+4 floats.
+template <int C, int M2>
+__device__ __forceinline__ void stage_windows(float* dst, const float* __restrict__ prow, int row0, int nrows,
+                                              int colbase, int L) {
+  constexpr int PIECES = C / 2 + 1, WP = 2 * C + 4;
+  for (int i = threadIdx.x; i < nrows * PIECES; i += blockDim.x) {
+    const int rr = i / PIECES, pc = i - rr * PIECES;
+    const int t = 2 * ((row0 + rr) * M2 + colbase) - 4 + 4 * pc;
+    const bool ok = (t >= 0) && (t + 4 <= L);
+    cp_async16(dst + rr * WP + 4 * pc, prow + (ok ? t : 0), ok);
+  }
+}
+// same without halo (pitch 2C floats)
+template <int C, int M2>
+__device__ __forceinline__ void stage_plain(float* dst, const float* __restrict__ prow, int row0, int nrows,
+                                            int colbase, int L) {
+  constexpr int PIECES = C / 2, XP = 2 * C;
+  for (int i = threadIdx.x; i < nrows * PIECES; i += blockDim.x) {
+    const int rr = i / PIECES, pc = i - rr * PIECES;
+    const int t = 2 * ((row0 + rr) * M2 + colbase) + 4 * pc;
+    const bool ok = (t + 4 <= L);
+    cp_async16(dst + rr * XP + 4 * pc, prow + (ok ? t : 0), ok);
+  }
+}
+// window of a staged row: P(t0-2..t0+1) with the in_proj bias added to in-range samples
+template <int C>
+__device__ __forceinline__ void staged_window(const float* st, int rr, int col, int t0, float ib, float (&P)[4]) {
+  const float* w = st + rr * (2 * C + 4) + 2 + 2 * col;
+  const float2 lo = *reinterpret_cast<const float2*>(w);
+  const float2 hi = *reinterpret_cast<const float2*>(w + 2);
+  const float lb = (t0 >= 2) ? ib : 0.f;             // samples before t = 0 are the conv padding: no bias
+  P[0] = lo.x + lb; P[1] = lo.y + lb; P[2] = hi.x + ib; P[3] = hi.y + ib;
+}
+template <int C>
+__device__ __forceinline__ float2 staged_pair(const float* st, int rr, int col) {
+  return *reinterpret_cast<const float2*>(st + rr * (2 * C) + 2 * col);
+}
+
 // ------------------------------------------------------------------------------------------------
 // argument blocks
 // ------------------------------------------------------------------------------------------------
@@ -96,6 +150,7 @@ struct PassArgs {
   int c0;           // first channel of this launch
   float scale;      // 1/(4M), applied by col_inv
   int vec;          // 1: L even and every row base 8-byte aligned -> float2 accesses
+  int stage;        // 1: L % 4 == 0 and every row base 16-byte aligned -> cp.async staging of column tiles
   Twiddles T;
   float2* A;        // scratch rows [r][k1][m2]
   float2* A2;       // second scratch (bwd: rows of g)
@@ -132,7 +187,17 @@ struct ColGeo {
   static constexpr int CTAS = M2 / C;                           // CTAs per row
   static constexpr int PAD = C >= 16 ? 1 : 16 / C;
   static constexpr int PITCH = TWO ? Geo<TWO ? LOGM1 : 5>::ex_elems() + PAD : 0;   // exchange elems per column
-  static constexpr size_t SMEM = (R2 > 1) ? (size_t)C * PITCH * sizeof(float2) : 0;
+  static constexpr size_t EXCH = (R2 > 1) ? (size_t)C * PITCH * sizeof(float2) : 0;
+  // cp.async staging (TWO only): forward needs two tensors of the M1/2 data rows; the inverse epilogue is
+  // staged four slots (4*R2 rows) at a time with up to five tensors
+  static constexpr int DATA_ROWS = M1 >= 2 ? M1 / 2 : 1;
+  static constexpr int WP = 2 * C + 4, XP = 2 * C;               // staged row pitches (floats): with / without halo
+  static constexpr int BATCH_ROWS = 4 * R2;
+  static constexpr size_t STAGE_FWD = TWO ? (size_t)DATA_ROWS * (WP + WP) * sizeof(float) : 0;
+  static constexpr size_t STAGE_INV = TWO ? (size_t)BATCH_ROWS * (3 * WP + 2 * XP) * sizeof(float) : 0;
+  static constexpr size_t SMEM_FWD = EXCH > STAGE_FWD ? EXCH : STAGE_FWD;
+  static constexpr size_t SMEM_INV = EXCH > STAGE_INV ? EXCH : STAGE_INV;
+  static constexpr size_t SMEM = EXCH;
   static_assert(C <= M2, "column tile wider than a row");
 };
 
@@ -192,12 +257,47 @@ col_fwd_kernel(const PassArgs a) {
     const int col = threadIdx.x % CG::C, q = threadIdx.x / CG::C;
     const int m2 = colbase + col;
     // slots n1 >= 16 (m1 >= M1/2) are the zero padding: never loaded
-    static_for<0, 16>([&](auto n_) {
-      constexpr int n1 = decltype(n_)::value;
-      const int m1 = CG::R2 * n1 + q;
-      const int t0 = 2 * (m1 * kM2 + m2);
-      v[n1] = (t0 < L) ? col_input<MODE>(a, b, c, t0, vec, ka, kb) : make_float2(0.f, 0.f);
-    });
+    if ((MODE == COL_GATE || MODE == COL_DC) && a.stage) {
+      float* st0 = reinterpret_cast<float*>(smem_raw);
+      float* st1 = st0 + CG::DATA_ROWS * CG::WP;
+      if constexpr (MODE == COL_GATE) {
+        stage_windows<CG::C, kM2>(st0, a.p + row_off(b, a.D + c, 3 * a.D, L), 0, CG::DATA_ROWS, colbase, L);
+        stage_windows<CG::C, kM2>(st1, a.p + row_off(b, 2 * a.D + c, 3 * a.D, L), 0, CG::DATA_ROWS, colbase, L);
+      } else {
+        stage_windows<CG::C, kM2>(st0, a.p + row_off(b, c, 3 * a.D, L), 0, CG::DATA_ROWS, colbase, L);
+        stage_plain<CG::C, kM2>(st1, a.src + row_off(b, c, a.D, L), 0, CG::DATA_ROWS, colbase, L);
+      }
+      cp_async_wait_all();
+      __syncthreads();
+      static_for<0, 16>([&](auto n_) {
+        constexpr int n1 = decltype(n_)::value;
+        const int m1 = CG::R2 * n1 + q;
+        const int t0 = 2 * (m1 * kM2 + m2);
+        float2 g = make_float2(0.f, 0.f);
+        if (t0 < L) {
+          float P[4];
+          staged_window<CG::C>(st0, m1, col, t0, ka.ib, P);
+          const float2 x = conv_window(P, t0, L, ka);
+          if constexpr (MODE == COL_GATE) {
+            staged_window<CG::C>(st1, m1, col, t0, kb.ib, P);
+            const float2 y = conv_window(P, t0, L, kb);
+            g = make_float2(x.x * y.x, x.y * y.y);
+          } else {
+            const float2 dy = staged_pair<CG::C>(st1, m1, col);
+            g = make_float2(x.x * dy.x, x.y * dy.y);
+          }
+        }
+        v[n1] = g;
+      });
+      __syncthreads();                                  // the staging area becomes the FFT exchange area
+    } else {
+      static_for<0, 16>([&](auto n_) {
+        constexpr int n1 = decltype(n_)::value;
+        const int m1 = CG::R2 * n1 + q;
+        const int t0 = 2 * (m1 * kM2 + m2);
+        v[n1] = (t0 < L) ? col_input<MODE>(a, b, c, t0, vec, ka, kb) : make_float2(0.f, 0.f);
+      });
+    }
     static_for<16, 32>([&](auto n_) { v[decltype(n_)::value] = make_float2(0.f, 0.f); });
     block_fft<CG::TWO ? LOGM1 : 5, false, true>(v, smem + col * CG::PITCH, q, a.T.tw1024, CtaSync{});
     // 4-step twiddle W_M^{m2*k1}, k1 = R2*s + q : geometric in s
@@ -349,26 +449,68 @@ col_inv_kernel(const PassArgs a) {
       v[n1] = Arow[(size_t)(CG::R2 * n1 + q) * kM2 + m2];
     });
     block_fft<CG::TWO ? LOGM1 : 5, true, false>(v, smem + col * CG::PITCH, q, a.T.tw1024, CtaSync{});
-    // only m1 < M1/2 (slots s < 16) can hold samples t < L; slots are handled four at a time with all
-    // their loads issued before the first dependent instruction
-    constexpr int NB = (MODE == INV_DK) ? 1 : 4;
-    static_for<0, 16 / NB>([&](auto g_) {
-      constexpr int s0 = decltype(g_)::value * NB;
-      InvIn in[NB];
-      static_for<0, NB>([&](auto j_) {
-        constexpr int j = decltype(j_)::value;
-        const int t0 = 2 * ((CG::R2 * (s0 + j) + q) * kM2 + m2);
-        if (t0 < L) inv_load<MODE>(a, cx, b, c, t0, vec, in[j]);
-      });
-      static_for<0, NB>([&](auto j_) {
-        constexpr int j = decltype(j_)::value;
-        const int t0 = 2 * ((CG::R2 * (s0 + j) + q) * kM2 + m2);
-        if (t0 < L) {
-          float2 y = v[Geo<CG::TWO ? LOGM1 : 5>::slot(s0 + j)];
-          inv_finish<MODE>(a, cx, b, c, t0, vec, make_float2(y.x * a.scale, y.y * a.scale), in[j]);
+    // only m1 < M1/2 (slots s < 16) can hold samples t < L
+    if ((MODE == INV_CONV_FWD || MODE == INV_BWD_DG) && a.stage) {
+      // epilogue operands staged through shared memory four slots (4*R2 consecutive rows) at a time
+      float* st = reinterpret_cast<float*>(smem_raw);
+      float* w0 = st;
+      float* w1 = w0 + CG::BATCH_ROWS * CG::WP;
+      float* w2 = w1 + CG::BATCH_ROWS * CG::WP;
+      float* x0 = w2 + CG::BATCH_ROWS * CG::WP;
+      float* x1 = x0 + CG::BATCH_ROWS * CG::XP;
+      static_for<0, 4>([&](auto g_) {
+        constexpr int s0 = decltype(g_)::value * 4;
+        const int row0 = CG::R2 * s0;
+        __syncthreads();                                // previous users of the area (FFT exchange / last batch) are done
+        stage_windows<CG::C, kM2>(w0, a.p + row_off(b, c, 3 * a.D, L), row0, CG::BATCH_ROWS, colbase, L);
+        stage_windows<CG::C, kM2>(w1, a.p + row_off(b, a.D + c, 3 * a.D, L), row0, CG::BATCH_ROWS, colbase, L);
+        stage_windows<CG::C, kM2>(w2, a.p + row_off(b, 2 * a.D + c, 3 * a.D, L), row0, CG::BATCH_ROWS, colbase, L);
+        if constexpr (MODE == INV_BWD_DG) {
+          stage_plain<CG::C, kM2>(x0, a.src + row_off(b, c, a.D, L), row0, CG::BATCH_ROWS, colbase, L);
+          stage_plain<CG::C, kM2>(x1, a.src2 + row_off(b, c, a.D, L), row0, CG::BATCH_ROWS, colbase, L);
         }
+        cp_async_wait_all();
+        __syncthreads();
+        static_for<0, 4>([&](auto j_) {
+          constexpr int j = decltype(j_)::value;
+          const int m1 = CG::R2 * (s0 + j) + q;
+          const int t0 = 2 * (m1 * kM2 + m2);
+          if (t0 < L) {
+            InvIn in;
+            const int rr = m1 - row0;
+            staged_window<CG::C>(w0, rr, col, t0, cx.k0.ib, in.P0);
+            staged_window<CG::C>(w1, rr, col, t0, cx.k1.ib, in.P1);
+            staged_window<CG::C>(w2, rr, col, t0, cx.k2.ib, in.P2);
+            if constexpr (MODE == INV_BWD_DG) {
+              in.a = staged_pair<CG::C>(x0, rr, col);
+              in.b = staged_pair<CG::C>(x1, rr, col);
+            }
+            float2 y = v[Geo<CG::TWO ? LOGM1 : 5>::slot(s0 + j)];
+            inv_finish<MODE>(a, cx, b, c, t0, vec, make_float2(y.x * a.scale, y.y * a.scale), in);
+          }
+        });
       });
-    });
+    } else {
+      // register path: slots are handled four at a time with all their loads issued before the first use
+      constexpr int NB = (MODE == INV_DK) ? 1 : 4;
+      static_for<0, 16 / NB>([&](auto g_) {
+        constexpr int s0 = decltype(g_)::value * NB;
+        InvIn in[NB];
+        static_for<0, NB>([&](auto j_) {
+          constexpr int j = decltype(j_)::value;
+          const int t0 = 2 * ((CG::R2 * (s0 + j) + q) * kM2 + m2);
+          if (t0 < L) inv_load<MODE>(a, cx, b, c, t0, vec, in[j]);
+        });
+        static_for<0, NB>([&](auto j_) {
+          constexpr int j = decltype(j_)::value;
+          const int t0 = 2 * ((CG::R2 * (s0 + j) + q) * kM2 + m2);
+          if (t0 < L) {
+            float2 y = v[Geo<CG::TWO ? LOGM1 : 5>::slot(s0 + j)];
+            inv_finish<MODE>(a, cx, b, c, t0, vec, make_float2(y.x * a.scale, y.y * a.scale), in[j]);
+          }
+        });
+      });
+    }
   } else {
     static_for<0, CG::G>([&](auto g_) {
       constexpr int gi = decltype(g_)::value;

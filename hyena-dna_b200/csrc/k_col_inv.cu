@@ -5,10 +5,10 @@ template <int LOGM1, int LOGM2, int MODE>
 static cudaError_t go(const PassArgs& a, int rows, cudaStream_t s) {
   using CG = ColGeo<LOGM1, LOGM2>;
   auto kern = col_inv_kernel<LOGM1, LOGM2, MODE>;
-  cudaError_t e = set_smem(kern, CG::SMEM);
+  cudaError_t e = set_smem(kern, CG::SMEM_INV);
   if (e != cudaSuccess) return e;
   prof_begin(K_COL_INV + MODE, s);
-  kern<<<dim3(CG::CTAS, rows), CG::THREADS, CG::SMEM, s>>>(a);
+  kern<<<dim3(CG::CTAS, rows), CG::THREADS, CG::SMEM_INV, s>>>(a);
   prof_end(K_COL_INV + MODE, s);
   return cudaGetLastError();
 }
@@ -25,6 +25,10 @@ static cudaError_t by_size(const PassArgs& a, int rows, cudaStream_t s) {
       case 4: return go<4, 10, MODE>(a, rows, s);
       case 5: return go<5, 10, MODE>(a, rows, s);
       case 6: return go<6, 10, MODE>(a, rows, s);
+      case 7: return go<7, 10, MODE>(a, rows, s);
+      case 8: return go<8, 10, MODE>(a, rows, s);
+      case 9: return go<9, 10, MODE>(a, rows, s);
+      case 10: return go<10, 10, MODE>(a, rows, s);
     }
   } else if (a.logM2 == 12) {
     switch (a.logM1) {
