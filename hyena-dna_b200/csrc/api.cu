@@ -99,12 +99,15 @@ static int log_m_for(int L) {         // M = 2^logM >= max(L, 1024)
   while (((size_t)1 << lg) < (size_t)L) ++lg;
   return lg;
 }
-// row length: 4096 for M >= 2^17 unless HYENA_B200_LOGM2=10 asks for 1024-point rows everywhere
+// Row length.  Both 1024- and 4096-point row kernels exist; measured on B200 at L = 2^20
+// (profiles/r1_config_sweep.txt) the 1024-point rows win overall (the 4096-point backward row pass holds
+// two spectra per thread group and spills), so 1024 is the default; HYENA_B200_LOGM2=12 selects 4096-point
+// rows for M >= 2^17.
 static int pick_log_m2(int logM) {
   static int forced = -1;
   if (forced < 0) { const char* e = getenv("HYENA_B200_LOGM2"); forced = e ? atoi(e) : 0; }
-  if (forced == 10) return 10;
-  return log_m2_for(logM);
+  if (forced == 12) return log_m2_for(logM);
+  return 10;
 }
 static size_t row_bytes(int L) { return ((size_t)1 << log_m_for(L)) * sizeof(float2); }
 
