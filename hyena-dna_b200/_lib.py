@@ -95,7 +95,7 @@ def profile_begin():
 
 def profile_end():
     """-> {kernel class: (device ms, launches)} for the window opened by profile_begin()."""
-    n = 16
+    n = 18
     ms = (ctypes.c_double * n)()
     cnt = (ctypes.c_ulonglong * n)()
     check(lib().hyena_b200_profile_end(ms, cnt, n))

@@ -214,7 +214,7 @@ HY_API const char* hyena_b200_kind_name(int kind) {
       "col_fwd<filter>", "col_fwd<gate>", "col_fwd<dc>", "col_fwd<plain>",
       "col_inv<conv_fwd>", "col_inv<bwd_dg>", "col_inv<dk>", "col_inv<plain_fwd>", "col_inv<plain_bwd>",
       "row_pass<filter>", "row_pass<conv_fwd>", "row_pass<conv_bwd>",
-      "filter_fwd", "filter_bwd", "short_conv_bwd", "twiddle_init"};
+      "filter_fwd", "filter_bwd", "short_conv_bwd", "twiddle_init", "filter_tc_prep", "filter_tc_fwd"};
   return (kind >= 0 && kind < K_COUNT) ? names[kind] : "?";
 }
 
@@ -256,7 +256,29 @@ HY_API int hyena_b200_filter_fwd(const float* z, int z_stride, const float* t, c
   if (fill_filter_params(&P, z, z_stride, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, shift, modulate, L, E, N, D))
     return 1;
   HY_CHECK(k_out, "null output");
-  HY_CUDA(launch_filter_fwd(P, k_out, (cudaStream_t)stream));
+  static const bool simt = getenv("HYENA_B200_FILTER") && !strcmp(getenv("HYENA_B200_FILTER"), "simt");
+  if (simt) {
+    HY_CUDA(launch_filter_fwd(P, k_out, (cudaStream_t)stream));
+    return 0;
+  }
+  // tensor-core path: per-device scratch for the tf32 hi/lo weight images (grow-only)
+  int dev = -1;
+  HY_CUDA(cudaGetDevice(&dev));
+  HY_CHECK(dev >= 0 && dev < 64, "unsupported device ordinal %d", dev);
+  float* wimg = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    static float* bufs[64] = {nullptr};
+    static size_t sizes[64] = {0};
+    const size_t need = filter_tc_wimg_bytes(D);
+    if (sizes[dev] < need) {
+      if (bufs[dev]) { HY_CUDA(cudaStreamSynchronize((cudaStream_t)stream)); HY_CUDA(cudaFree(bufs[dev])); }
+      HY_CUDA(cudaMalloc(&bufs[dev], need));
+      sizes[dev] = need;
+    }
+    wimg = bufs[dev];
+  }
+  HY_CUDA(launch_filter_fwd_tc(P, wimg, k_out, (cudaStream_t)stream));
   return 0;
 }
 

@@ -1,0 +1,322 @@
+// Implicit-filter forward on the 5th-generation tensor cores (tcgen05 / TMEM), sm_100a only.
+//
+// Same math as filter_fwd_kernel (filter_mlp.cuh; reference src/models/sequence/hyena.py:96-155,199-238),
+// but the three GEMM-shaped layers run as tcgen05.mma.kind::tf32 with fp32 accumulators in tensor memory:
+//
+//   tile = 128 positions (UMMA M = 128, one TMEM lane per position, one thread per lane in the epilogues)
+//   layer 1,2 : D[128 x 64]  = act[128 x 64] * W^T      (N = 64,  K = 64)
+//   layer 3   : D[128 x 128] = act[128 x 64] * W3_h^T   (N = 128, K = 64) per half of 128 channels
+//
+// fp32 accuracy on tf32 tensor cores: every fp32 operand x is split x = hi + lo with hi = rna_tf32(x),
+// lo = rna_tf32(x - hi), and each product is issued three times (hi*hi + lo*hi + hi*lo, the lo*lo term is
+// below 2^-22 relative): "3xTF32".  Plain TF32 would put ~5e-4 relative error into k and hence into y.
+//
+// Operands are written to shared memory by the CUDA cores (the activations are produced in registers by the
+// previous epilogue, so there is nothing for TMA to fetch) in the canonical no-swizzle K-major core-matrix
+// layout: element (r, k) of an R x 64 fp32 operand sits at byte (r/8)*2048 + (k/4)*128 + (r%8)*16 + (k%4)*4,
+// i.e. 8-row x 16-byte core matrices, LBO (K direction) = 128 B, SBO (M/N direction) = 2048 B.
+// One elected thread issues the MMAs; completion is tracked with tcgen05.commit -> mbarrier.
+#pragma once
+#include "fft_passes.cuh"
+#include "filter_mlp.cuh"
+
+namespace hy {
+namespace tc {
+
+constexpr int kTileM = 128;
+constexpr uint32_t kSBO = 2048, kLBO = 128;
+constexpr int kImgW64 = 64 * 64;            // floats of a 64-row operand image
+constexpr int kImgW128 = 128 * 64;          // floats of a 128-row operand image
+constexpr int kTmemCols = 256;              // [0,64) hidden-layer accumulator, [64,192) output half accumulator
+
+__host__ __device__ constexpr uint32_t op_off(int r, int k) {   // byte offset inside an operand image
+  return (uint32_t)((r >> 3) * 2048 + (k >> 2) * 128 + (r & 7) * 16 + (k & 3) * 4);
+}
+
+// shared memory map (bytes)
+constexpr uint32_t kOffAhi = 0, kOffAlo = 32768, kOffW1hi = 65536, kOffW1lo = 81920, kOffW2hi = 98304,
+                   kOffW2lo = 114688, kOffW3hi = 131072, kOffW3lo = 163840, kOffMisc = 196608;
+// misc: W0[64][16] | b0[64] | b1[64] | b2[64] | freq[64] | mbar(8) | tmem_ptr(4)
+constexpr uint32_t kMiscFloats = 64 * 16 + 4 * 64;
+constexpr size_t kSmemBytes = kOffMisc + kMiscFloats * 4 + 16;
+
+__host__ __device__ constexpr size_t wimg_floats(int D) { return 4 * (size_t)kImgW64 + (size_t)((D + 127) / 128) * 2 * kImgW128; }
+
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = to_tf32(x);
+  lo = to_tf32(x - hi);
+}
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);            // start address, 16-byte units, bits [0,14)
+  d |= (uint64_t)(kLBO >> 4) << 16;                    // leading (K) byte offset, bits [16,30)
+  d |= (uint64_t)(kSBO >> 4) << 32;                    // stride (M/N) byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                              // descriptor version 1 (Blackwell)
+  return d;                                            // base_offset 0, layout_type 0 (no swizzle)
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128
+__host__ __device__ constexpr uint32_t make_idesc(int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t}\n"
+      ::"r"(mbar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 32 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// D[128 x N] (+)= A * B^T as 3xTF32: 24 MMAs of K = 8, issued by the calling (single) thread
+__device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                            int N, uint32_t mbar) {
+  const uint32_t idesc = make_idesc(N);
+  uint32_t acc = 0;
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {
+    const uint32_t a = (pass == 1) ? a_lo : a_hi;
+    const uint32_t b = (pass == 2) ? b_lo : b_hi;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      mma_tf32(tmem_d, make_desc(a + ks * 2 * kLBO), make_desc(b + ks * 2 * kLBO), idesc, acc);
+      acc = 1;
+    }
+  }
+  mma_commit(mbar);
+}
+
+// write 64 activations of row `row` (this thread's position) as hi/lo operand images
+__device__ __forceinline__ void store_row_split(unsigned char* smem, int row, int k0, const float (&a)[32]) {
+#pragma unroll
+  for (int kc = 0; kc < 8; ++kc) {
+    float4 hi, lo;
+    split_tf32(a[4 * kc + 0], hi.x, lo.x);
+    split_tf32(a[4 * kc + 1], hi.y, lo.y);
+    split_tf32(a[4 * kc + 2], hi.z, lo.z);
+    split_tf32(a[4 * kc + 3], hi.w, lo.w);
+    const uint32_t off = op_off(row, k0 + 4 * kc);
+    *reinterpret_cast<float4*>(smem + kOffAhi + off) = hi;
+    *reinterpret_cast<float4*>(smem + kOffAlo + off) = lo;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- prep
+// Split the weights into tf32 hi/lo operand images (global memory, in shared-memory image order):
+// [W1 hi][W1 lo][W2 hi][W2 lo] then per 128-channel half h: [W3_h hi][W3_h lo] (rows >= D are zero).
+__global__ void filter_tc_prep_kernel(const float* __restrict__ W1, const float* __restrict__ W2,
+                                      const float* __restrict__ W3, int D, float* __restrict__ wimg) {
+  const int nh = (D + 127) / 128;
+  const int total = 2 * kImgW64 + nh * kImgW128;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    float x;
+    float* hi_img;
+    float* lo_img;
+    int r, k;
+    if (i < 2 * kImgW64) {
+      const int w = i / kImgW64, e = i % kImgW64;
+      r = e / 64; k = e % 64;
+      x = (w == 0 ? W1 : W2)[r * 64 + k];
+      hi_img = wimg + w * 2 * kImgW64;
+      lo_img = hi_img + kImgW64;
+    } else {
+      const int j = i - 2 * kImgW64, h = j / kImgW128, e = j % kImgW128;
+      r = e / 64; k = e % 64;
+      const int c = h * 128 + r;
+      x = (c < D) ? W3[(size_t)c * 64 + k] : 0.f;
+      hi_img = wimg + 4 * kImgW64 + (size_t)h * 2 * kImgW128;
+      lo_img = hi_img + kImgW128;
+    }
+    float hi, lo;
+    split_tf32(x, hi, lo);
+    hi_img[op_off(r, k) / 4] = hi;
+    lo_img[op_off(r, k) / 4] = lo;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- forward
+__global__ void __launch_bounds__(128, 1)
+filter_tc_fwd_kernel(const FilterParams P, const float* __restrict__ wimg, float* __restrict__ kout, int ntiles) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  float* misc = reinterpret_cast<float*>(smem + kOffMisc);
+  float* W0s = misc;                    // [64][16]
+  float* b0s = misc + 64 * 16;
+  float* b1s = b0s + 64;
+  float* b2s = b1s + 64;
+  float* frs = b2s + 64;
+  uint64_t* mbar_p = reinterpret_cast<uint64_t*>(frs + 64);
+  uint32_t* tmem_p = reinterpret_cast<uint32_t*>(mbar_p + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t mbar = smem_u32(mbar_p);
+  const int nh = (P.D + 127) / 128;
+
+  // ---- one-time setup: TMEM allocation, mbarrier, resident weights
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_p)), "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) mbar_init(mbar, 1);
+  for (int i = tid; i < 4 * kImgW64 / 4; i += 128)       // W1/W2 hi/lo images: 64 KB, 16 bytes per cp.async
+    cp_async16(smem + kOffW1hi + 16 * i, wimg + 4 * i, true);
+  for (int i = tid; i < 64 * 16; i += 128) {
+    const int r = i / 16, e = i % 16;
+    W0s[i] = (e < P.E) ? __ldg(P.W0 + r * P.E + e) : 0.f;
+  }
+  if (tid < 64) {
+    b0s[tid] = __ldg(P.b0 + tid); b1s[tid] = __ldg(P.b1 + tid); b2s[tid] = __ldg(P.b2 + tid);
+    frs[tid] = __ldg(P.freq + tid);
+  }
+  cp_async_wait_all();
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tmem_p;
+  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);       // this warp's 32 TMEM lanes
+  uint32_t phase = 0;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int t = tile * kTileM + tid;
+    const bool tv = t < P.L;
+    // prefetch output-layer half 0 (the buffer is free: the MMAs that read it completed last tile)
+    {
+      const float* src = wimg + 4 * kImgW64;
+      for (int i = tid; i < 2 * kImgW128 / 4; i += 128) cp_async16(smem + kOffW3hi + 16 * i, src + 4 * i, true);
+    }
+    // ---- layer 0 on the CUDA cores: a1 = sin(f * (W0 z + b0))
+    {
+      float z[kMaxE];
+#pragma unroll
+      for (int e = 0; e < kMaxE; ++e) z[e] = (tv && e < P.E) ? __ldg(P.z + (size_t)t * P.z_stride + e) : 0.f;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float a[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int i = half * 32 + j;
+          float acc = b0s[i];
+#pragma unroll
+          for (int e = 0; e < kMaxE; ++e) acc = fmaf(W0s[i * 16 + e], z[e], acc);
+          a[j] = sinf(frs[i] * acc);
+        }
+        store_row_split(smem, tid, half * 32, a);
+      }
+    }
+    fence_async_smem();
+    __syncthreads();
+    // ---- layers 1 and 2 on the tensor cores
+#pragma unroll
+    for (int layer = 0; layer < 2; ++layer) {
+      if (tid == 0) {
+        fence_after_sync();
+        issue_layer(tmem, sbase + kOffAhi, sbase + kOffAlo, sbase + (layer ? kOffW2hi : kOffW1hi),
+                    sbase + (layer ? kOffW2lo : kOffW1lo), 64, mbar);
+      }
+      mbar_wait(mbar, phase);
+      phase ^= 1;
+      fence_after_sync();
+      const float* bs = layer ? b2s : b1s;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float a[32];
+        tmem_ld32(lane_addr + half * 32, a);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a[j] = sinf(frs[half * 32 + j] * (a[j] + bs[half * 32 + j]));
+        store_row_split(smem, tid, half * 32, a);       // the MMAs that read the A images have completed
+      }
+      fence_before_sync();
+      fence_async_smem();
+      __syncthreads();
+    }
+    // ---- output layer, 128 channels at a time, modulation in the epilogue
+    const float tpos = tv ? __ldg(P.t + t) : 0.f;
+    for (int h = 0; h < nh; ++h) {
+      cp_async_wait_all();                               // this thread's pieces of half h have landed
+      fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        fence_after_sync();
+        issue_layer(tmem + 64, sbase + kOffAhi, sbase + kOffAlo, sbase + kOffW3hi, sbase + kOffW3lo, 128, mbar);
+      }
+      mbar_wait(mbar, phase);
+      phase ^= 1;
+      fence_after_sync();
+      if (h + 1 < nh) {                                  // stream the next half while this one is written out
+        const float* src = wimg + 4 * kImgW64 + (size_t)(h + 1) * 2 * kImgW128;
+        for (int i = tid; i < 2 * kImgW128 / 4; i += 128) cp_async16(smem + kOffW3hi + 16 * i, src + 4 * i, true);
+      }
+#pragma unroll 1
+      for (int chunk = 0; chunk < 4; ++chunk) {
+        float v[32];
+        tmem_ld32(lane_addr + 64 + chunk * 32, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int c = h * 128 + chunk * 32 + j;
+          if (c < P.D && tv) {
+            float x = v[j];
+            if (P.modulate) x *= (expf(-tpos * fabsf(__ldg(P.deltas + c))) + P.shift);
+            kout[(size_t)c * P.L + t] = x;
+          }
+        }
+      }
+      fence_before_sync();
+    }
+    __syncthreads();                                     // A images and TMEM are free for the next tile
+  }
+
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+  }
+}
+
+}  // namespace tc
+}  // namespace hy

@@ -1,0 +1,26 @@
+#include "launch.h"
+#include "filter_tc.cuh"
+namespace hy {
+
+size_t filter_tc_wimg_bytes(int D) { return tc::wimg_floats(D) * sizeof(float); }
+
+cudaError_t launch_filter_fwd_tc(const FilterParams& P, float* wimg, float* kout, cudaStream_t s) {
+  cudaError_t e = set_smem(tc::filter_tc_fwd_kernel, tc::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  prof_begin(K_FILTER_TC_PREP, s);
+  tc::filter_tc_prep_kernel<<<64, 256, 0, s>>>(P.W1, P.W2, P.W3, P.D, wimg);
+  prof_end(K_FILTER_TC_PREP, s);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int ntiles = (P.L + tc::kTileM - 1) / tc::kTileM;
+  const int grid = ntiles < sms ? ntiles : sms;
+  prof_begin(K_FILTER_TC_FWD, s);
+  tc::filter_tc_fwd_kernel<<<grid, 128, tc::kSmemBytes, s>>>(P, wimg, kout, ntiles);
+  prof_end(K_FILTER_TC_FWD, s);
+  return cudaGetLastError();
+}
+
+}  // namespace hy
