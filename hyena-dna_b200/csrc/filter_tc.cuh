@@ -114,6 +114,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // D[128 x N] (+)= A * B^T as 3xTF32: 24 MMAs of K = 8, issued by the calling (single) thread
 __device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
                                             int N, uint32_t mbar) {
@@ -132,10 +146,11 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_hi, uint
   mma_commit(mbar);
 }
 
-// write 64 activations of row `row` (this thread's position) as hi/lo operand images
-__device__ __forceinline__ void store_row_split(unsigned char* smem, int row, int k0, const float (&a)[32]) {
+// write NV activations (features k0 .. k0+NV) of row `row` as hi/lo operand images
+template <int NV>
+__device__ __forceinline__ void store_row_split(unsigned char* smem, int row, int k0, const float (&a)[NV]) {
 #pragma unroll
-  for (int kc = 0; kc < 8; ++kc) {
+  for (int kc = 0; kc < NV / 4; ++kc) {
     float4 hi, lo;
     split_tf32(a[4 * kc + 0], hi.x, lo.x);
     split_tf32(a[4 * kc + 1], hi.y, lo.y);
@@ -181,7 +196,11 @@ __global__ void filter_tc_prep_kernel(const float* __restrict__ W1, const float*
 }
 
 // ---------------------------------------------------------------------------------------------- forward
-__global__ void __launch_bounds__(128, 1)
+// 512 threads: warp w works on TMEM lanes 32*(w%4).. (positions) and on column part w/4 of every accumulator,
+// so four warps per scheduler hide the latency of the sin/exp epilogues.
+constexpr int kThreads = 512;
+
+__global__ void __launch_bounds__(kThreads, 1)
 filter_tc_fwd_kernel(const FilterParams P, const float* __restrict__ wimg, float* __restrict__ kout, int ntiles) {
   extern __shared__ __align__(1024) unsigned char smem[];
   float* misc = reinterpret_cast<float*>(smem + kOffMisc);
@@ -192,7 +211,9 @@ filter_tc_fwd_kernel(const FilterParams P, const float* __restrict__ wimg, float
   float* frs = b2s + 64;
   uint64_t* mbar_p = reinterpret_cast<uint64_t*>(frs + 64);
   uint32_t* tmem_p = reinterpret_cast<uint32_t*>(mbar_p + 1);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int part = warp >> 2;                             // which quarter of the columns
+  const int row = 32 * (warp & 3) + lane;                 // position inside the tile == TMEM lane
   const uint32_t sbase = smem_u32(smem);
   const uint32_t mbar = smem_u32(mbar_p);
   const int nh = (P.D + 127) / 128;
@@ -204,9 +225,9 @@ filter_tc_fwd_kernel(const FilterParams P, const float* __restrict__ wimg, float
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) mbar_init(mbar, 1);
-  for (int i = tid; i < 4 * kImgW64 / 4; i += 128)       // W1/W2 hi/lo images: 64 KB, 16 bytes per cp.async
+  for (int i = tid; i < 4 * kImgW64 / 4; i += kThreads)   // W1/W2 hi/lo images: 64 KB, 16 bytes per cp.async
     cp_async16(smem + kOffW1hi + 16 * i, wimg + 4 * i, true);
-  for (int i = tid; i < 64 * 16; i += 128) {
+  for (int i = tid; i < 64 * 16; i += kThreads) {
     const int r = i / 16, e = i % 16;
     W0s[i] = (e < P.E) ? __ldg(P.W0 + r * P.E + e) : 0.f;
   }
@@ -220,35 +241,32 @@ filter_tc_fwd_kernel(const FilterParams P, const float* __restrict__ wimg, float
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = *tmem_p;
-  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);       // this warp's 32 TMEM lanes
+  const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);   // this warp's 32 TMEM lanes
   uint32_t phase = 0;
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int t = tile * kTileM + tid;
+    const int t = tile * kTileM + row;
     const bool tv = t < P.L;
     // prefetch output-layer half 0 (the buffer is free: the MMAs that read it completed last tile)
     {
       const float* src = wimg + 4 * kImgW64;
-      for (int i = tid; i < 2 * kImgW128 / 4; i += 128) cp_async16(smem + kOffW3hi + 16 * i, src + 4 * i, true);
+      for (int i = tid; i < 2 * kImgW128 / 4; i += kThreads) cp_async16(smem + kOffW3hi + 16 * i, src + 4 * i, true);
     }
-    // ---- layer 0 on the CUDA cores: a1 = sin(f * (W0 z + b0))
+    // ---- layer 0 on the CUDA cores: a1 = sin(f * (W0 z + b0)), 16 features per thread
     {
       float z[kMaxE];
 #pragma unroll
       for (int e = 0; e < kMaxE; ++e) z[e] = (tv && e < P.E) ? __ldg(P.z + (size_t)t * P.z_stride + e) : 0.f;
+      float a[16];
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float a[32];
+      for (int j = 0; j < 16; ++j) {
+        const int i = part * 16 + j;
+        float acc = b0s[i];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int i = half * 32 + j;
-          float acc = b0s[i];
-#pragma unroll
-          for (int e = 0; e < kMaxE; ++e) acc = fmaf(W0s[i * 16 + e], z[e], acc);
-          a[j] = sinf(frs[i] * acc);
-        }
-        store_row_split(smem, tid, half * 32, a);
+        for (int e = 0; e < kMaxE; ++e) acc = fmaf(W0s[i * 16 + e], z[e], acc);
+        a[j] = sinf(frs[i] * acc);
       }
+      store_row_split<16>(smem, row, part * 16, a);
     }
     fence_async_smem();
     __syncthreads();
@@ -264,14 +282,11 @@ filter_tc_fwd_kernel(const FilterParams P, const float* __restrict__ wimg, float
       phase ^= 1;
       fence_after_sync();
       const float* bs = layer ? b2s : b1s;
+      float a[16];
+      tmem_ld16(lane_addr + part * 16, a);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float a[32];
-        tmem_ld32(lane_addr + half * 32, a);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) a[j] = sinf(frs[half * 32 + j] * (a[j] + bs[half * 32 + j]));
-        store_row_split(smem, tid, half * 32, a);       // the MMAs that read the A images have completed
-      }
+      for (int j = 0; j < 16; ++j) a[j] = sinf(frs[part * 16 + j] * (a[j] + bs[part * 16 + j]));
+      store_row_split<16>(smem, row, part * 16, a);        // the MMAs that read the A images have completed
       fence_before_sync();
       fence_async_smem();
       __syncthreads();
@@ -291,20 +306,17 @@ filter_tc_fwd_kernel(const FilterParams P, const float* __restrict__ wimg, float
       fence_after_sync();
       if (h + 1 < nh) {                                  // stream the next half while this one is written out
         const float* src = wimg + 4 * kImgW64 + (size_t)(h + 1) * 2 * kImgW128;
-        for (int i = tid; i < 2 * kImgW128 / 4; i += 128) cp_async16(smem + kOffW3hi + 16 * i, src + 4 * i, true);
+        for (int i = tid; i < 2 * kImgW128 / 4; i += kThreads) cp_async16(smem + kOffW3hi + 16 * i, src + 4 * i, true);
       }
-#pragma unroll 1
-      for (int chunk = 0; chunk < 4; ++chunk) {
-        float v[32];
-        tmem_ld32(lane_addr + 64 + chunk * 32, v);
+      float v[32];
+      tmem_ld32(lane_addr + 64 + part * 32, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int c = h * 128 + chunk * 32 + j;
-          if (c < P.D && tv) {
-            float x = v[j];
-            if (P.modulate) x *= (expf(-tpos * fabsf(__ldg(P.deltas + c))) + P.shift);
-            kout[(size_t)c * P.L + t] = x;
-          }
+      for (int j = 0; j < 32; ++j) {
+        const int c = h * 128 + part * 32 + j;
+        if (c < P.D && tv) {
+          float x = v[j];
+          if (P.modulate) x *= (expf(-tpos * fabsf(__ldg(P.deltas + c))) + P.shift);
+          kout[(size_t)c * P.L + t] = x;
         }
       }
       fence_before_sync();

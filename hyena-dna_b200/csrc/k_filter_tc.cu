@@ -18,7 +18,7 @@ cudaError_t launch_filter_fwd_tc(const FilterParams& P, float* wimg, float* kout
   const int ntiles = (P.L + tc::kTileM - 1) / tc::kTileM;
   const int grid = ntiles < sms ? ntiles : sms;
   prof_begin(K_FILTER_TC_FWD, s);
-  tc::filter_tc_fwd_kernel<<<grid, 128, tc::kSmemBytes, s>>>(P, wimg, kout, ntiles);
+  tc::filter_tc_fwd_kernel<<<grid, tc::kThreads, tc::kSmemBytes, s>>>(P, wimg, kout, ntiles);
   prof_end(K_FILTER_TC_FWD, s);
   return cudaGetLastError();
 }
