@@ -214,7 +214,7 @@ HY_API const char* hyena_b200_kind_name(int kind) {
       "col_fwd<filter>", "col_fwd<gate>", "col_fwd<dc>", "col_fwd<plain>",
       "col_inv<conv_fwd>", "col_inv<bwd_dg>", "col_inv<dk>", "col_inv<plain_fwd>", "col_inv<plain_bwd>",
       "row_pass<filter>", "row_pass<conv_fwd>", "row_pass<conv_bwd>",
-      "filter_fwd", "filter_bwd", "short_conv_bwd", "twiddle_init", "filter_tc_prep", "filter_tc_fwd"};
+      "filter_fwd", "filter_bwd", "short_conv_bwd", "twiddle_init", "filter_tc_prep", "filter_tc_fwd", "filter_tc_bwd"};
   return (kind >= 0 && kind < K_COUNT) ? names[kind] : "?";
 }
 
@@ -231,6 +231,24 @@ HY_API size_t hyena_b200_workspace_bytes(int B, int D, int L, int backward) {
   int nch = channels_per_group(group_budget_bytes(), B, D, L);
   if (nch < 1) nch = 1;
   return hyena_b200_workspace_min_bytes(B, D, L, backward) * (size_t)nch;
+}
+
+// tensor-core filter path: per-device scratch for the tf32 hi/lo weight images (grow-only)
+static int get_wimg(int D, cudaStream_t stream, float** out) {
+  int dev = -1;
+  HY_CUDA(cudaGetDevice(&dev));
+  HY_CHECK(dev >= 0 && dev < 64, "unsupported device ordinal %d", dev);
+  std::lock_guard<std::mutex> lk(g_mu);
+  static float* bufs[64] = {nullptr};
+  static size_t sizes[64] = {0};
+  const size_t need = filter_tc_wimg_bytes(D);
+  if (sizes[dev] < need) {
+    if (bufs[dev]) { HY_CUDA(cudaStreamSynchronize(stream)); HY_CUDA(cudaFree(bufs[dev])); }
+    HY_CUDA(cudaMalloc(&bufs[dev], need));
+    sizes[dev] = need;
+  }
+  *out = bufs[dev];
+  return 0;
 }
 
 static int fill_filter_params(FilterParams* P, const float* z, int z_stride, const float* t, const float* W0,
@@ -261,23 +279,8 @@ HY_API int hyena_b200_filter_fwd(const float* z, int z_stride, const float* t, c
     HY_CUDA(launch_filter_fwd(P, k_out, (cudaStream_t)stream));
     return 0;
   }
-  // tensor-core path: per-device scratch for the tf32 hi/lo weight images (grow-only)
-  int dev = -1;
-  HY_CUDA(cudaGetDevice(&dev));
-  HY_CHECK(dev >= 0 && dev < 64, "unsupported device ordinal %d", dev);
   float* wimg = nullptr;
-  {
-    std::lock_guard<std::mutex> lk(g_mu);
-    static float* bufs[64] = {nullptr};
-    static size_t sizes[64] = {0};
-    const size_t need = filter_tc_wimg_bytes(D);
-    if (sizes[dev] < need) {
-      if (bufs[dev]) { HY_CUDA(cudaStreamSynchronize((cudaStream_t)stream)); HY_CUDA(cudaFree(bufs[dev])); }
-      HY_CUDA(cudaMalloc(&bufs[dev], need));
-      sizes[dev] = need;
-    }
-    wimg = bufs[dev];
-  }
+  if (get_wimg(D, (cudaStream_t)stream, &wimg)) return 1;
   HY_CUDA(launch_filter_fwd_tc(P, wimg, k_out, (cudaStream_t)stream));
   return 0;
 }
@@ -293,6 +296,20 @@ HY_API int hyena_b200_filter_bwd(const float* z, int z_stride, const float* t, c
   HY_CHECK(dk && dW0 && db0 && dW1 && db1 && dW2 && db2 && dW3 && dfreq, "null gradient pointer");
   FilterGrads G{dW0, db0, dW1, db1, dW2, db2, dW3, dfreq, dz, dz_stride};
   HY_CUDA(launch_filter_bwd(P, dk, G, (cudaStream_t)stream));
+  return 0;
+}
+
+HY_API int hyena_b200_filter_bwd_stage1(const float* z, int z_stride, const float* t, const float* W0, const float* b0,
+                                 const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
+                                 const float* freq, const float* deltas, float shift, int modulate, int L, int E,
+                                 int N, int D, const float* dk, float* dh, float* scratch, void* stream) {
+  FilterParams P;
+  if (fill_filter_params(&P, z, z_stride, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, shift, modulate, L, E, N, D))
+    return 1;
+  HY_CHECK(dk && dh && scratch && ((reinterpret_cast<uintptr_t>(scratch) & 15u) == 0), "null or misaligned pointer");
+  float* wimg = nullptr;
+  if (get_wimg(D, (cudaStream_t)stream, &wimg)) return 1;
+  HY_CUDA(launch_filter_bwd_tc(P, wimg, dk, dh, scratch, (cudaStream_t)stream));
   return 0;
 }
 

@@ -330,5 +330,259 @@ filter_tc_fwd_kernel(const FilterParams P, const float* __restrict__ wimg, float
   }
 }
 
+// ---------------------------------------------------------------------------------------------- backward, stage 1
+// Per 128-position tile, all GEMMs with M = positions (thread = position, same operand builders as forward):
+//   recompute pre1..3 / a1..3;  da3 = dh W3 (dh = dk * modulation, K = channels in chunks of 64);
+//   dp3 = da3 f cos(f pre3);  da2 = dp3 W2;  dp2 = ...;  da1 = dp2 W1;  dp1 = ...
+// and writes, position-major [t][64]: a1, a2, a3, dp1, dp2, dp3, X = sum_l da_l cos(f pre_l) pre_l, plus dh (D, L).
+// Stage 2 (host side, hyena-dna_b200/ops.py) turns those into the parameter gradients with GEMMs whose reduction
+// dimension is the sequence: dW3 = dh a3, dW2 = dp3^T a2, dW1 = dp2^T a1, dW0 = dp1^T z, db_l = colsum(dp_l),
+// dfreq = colsum(X), dz = dp1 W0.
+//
+// Streamed operand images (global, built by filter_tc_prep_bwd_kernel), item i lives in stream buffer i & 1:
+//   items 0..nq-1: W3^T chunk q  [64 features x 64 channels of chunk q];  item nq: W2^T;  item nq+1: W1^T
+constexpr int kScratchArrays = 7;
+
+__host__ __device__ constexpr size_t wimg_bwd_floats(int D) {
+  return 4 * (size_t)kImgW64 + (size_t)((D + 63) / 64 + 2) * 2 * kImgW64;
+}
+
+__global__ void filter_tc_prep_bwd_kernel(const float* __restrict__ W1, const float* __restrict__ W2,
+                                          const float* __restrict__ W3, int D, float* __restrict__ wimg) {
+  const int nq = (D + 63) / 64;
+  const int total = (2 + nq + 2) * kImgW64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int item = i / kImgW64, e = i % kImgW64;
+    const int r = e / 64, k = e % 64;
+    float x;
+    float* hi_img = wimg + (size_t)item * 2 * kImgW64;
+    if (item == 0) x = W1[r * 64 + k];
+    else if (item == 1) x = W2[r * 64 + k];
+    else if (item < 2 + nq) {                  // W3^T chunk q: (feature r, channel k of the chunk)
+      const int c = (item - 2) * 64 + k;
+      x = (c < D) ? W3[(size_t)c * 64 + r] : 0.f;
+    } else if (item == 2 + nq) x = W2[k * 64 + r];     // W2^T
+    else x = W1[k * 64 + r];                           // W1^T
+    float hi, lo;
+    split_tf32(x, hi, lo);
+    hi_img[op_off(r, k) / 4] = hi;
+    hi_img[kImgW64 + op_off(r, k) / 4] = lo;
+  }
+}
+
+__device__ __forceinline__ void stream_item(unsigned char* smem, const float* wimg, int item, int tid) {
+  const float* src = wimg + (size_t)(2 + item) * 2 * kImgW64;
+  unsigned char* dst = smem + kOffW3hi + (item & 1) * 32768;
+  for (int i = tid; i < 2 * kImgW64 / 4; i += kThreads) cp_async16(dst + 16 * i, src + 4 * i, true);
+}
+
+__device__ __forceinline__ void store16(float* dst, const float (&a)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const float* __restrict__ dk,
+                     float* __restrict__ dh, float* __restrict__ scratch, int ntiles) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  float* misc = reinterpret_cast<float*>(smem + kOffMisc);
+  float* W0s = misc;
+  float* b0s = misc + 64 * 16;
+  float* b1s = b0s + 64;
+  float* b2s = b1s + 64;
+  float* frs = b2s + 64;
+  uint64_t* mbar_p = reinterpret_cast<uint64_t*>(frs + 64);
+  uint32_t* tmem_p = reinterpret_cast<uint32_t*>(mbar_p + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int part = warp >> 2;
+  const int row = 32 * (warp & 3) + lane;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t mbar = smem_u32(mbar_p);
+  const int nq = (P.D + 63) / 64;
+  const size_t arr = (size_t)P.L * 64;                   // floats per scratch array
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_p)), "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) mbar_init(mbar, 1);
+  for (int i = tid; i < 4 * kImgW64 / 4; i += kThreads) cp_async16(smem + kOffW1hi + 16 * i, wimg + 4 * i, true);
+  for (int i = tid; i < 64 * 16; i += kThreads) {
+    const int r = i / 16, e = i % 16;
+    W0s[i] = (e < P.E) ? __ldg(P.W0 + r * P.E + e) : 0.f;
+  }
+  if (tid < 64) {
+    b0s[tid] = __ldg(P.b0 + tid); b1s[tid] = __ldg(P.b1 + tid); b2s[tid] = __ldg(P.b2 + tid);
+    frs[tid] = __ldg(P.freq + tid);
+  }
+  cp_async_wait_all();
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tmem_p;
+  const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+  uint32_t phase = 0;
+  const float* fr = frs + part * 16;                      // this thread's 16 frequencies (shared memory)
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int t = tile * kTileM + row;
+    const bool tv = t < P.L;
+    float* out = scratch + (size_t)(tv ? t : 0) * 64 + part * 16;
+    stream_item(smem, wimg, 0, tid);
+    stream_item(smem, wimg, 1, tid);
+
+    // ---- forward recompute
+    float pre1[16], pre2[16], pre3[16], a[16];
+    {
+      float z[kMaxE];
+#pragma unroll
+      for (int e = 0; e < kMaxE; ++e) z[e] = (tv && e < P.E) ? __ldg(P.z + (size_t)t * P.z_stride + e) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int i = part * 16 + j;
+        float acc = b0s[i];
+#pragma unroll
+        for (int e = 0; e < kMaxE; ++e) acc = fmaf(W0s[i * 16 + e], z[e], acc);
+        pre1[j] = acc;
+        a[j] = sinf(fr[j] * acc);
+      }
+      store_row_split<16>(smem, row, part * 16, a);
+      if (tv) store16(out + 0 * arr, a);
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      issue_layer(tmem, sbase + kOffAhi, sbase + kOffAlo, sbase + kOffW1hi, sbase + kOffW1lo, 64, mbar);
+    }
+    mbar_wait(mbar, phase); phase ^= 1;
+    fence_after_sync();
+    tmem_ld16(lane_addr + part * 16, pre2);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { pre2[j] += b1s[part * 16 + j]; a[j] = sinf(fr[j] * pre2[j]); }
+    store_row_split<16>(smem, row, part * 16, a);
+    if (tv) store16(out + 1 * arr, a);
+    fence_before_sync();
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      issue_layer(tmem, sbase + kOffAhi, sbase + kOffAlo, sbase + kOffW2hi, sbase + kOffW2lo, 64, mbar);
+    }
+    mbar_wait(mbar, phase); phase ^= 1;
+    fence_after_sync();
+    tmem_ld16(lane_addr + part * 16, pre3);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { pre3[j] += b2s[part * 16 + j]; a[j] = sinf(fr[j] * pre3[j]); }
+    if (tv) store16(out + 2 * arr, a);
+    fence_before_sync();
+
+    // ---- da3 = dh W3, 64 channels per MMA group; dh = dk * (exp(-t|delta|) + shift) also goes to HBM (stage 2 needs it)
+    const float tpos = tv ? __ldg(P.t + t) : 0.f;
+    for (int q = 0; q < nq; ++q) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int c = q * 64 + part * 16 + j;
+        float x = 0.f;
+        if (c < P.D && tv) {
+          x = __ldg(dk + (size_t)c * P.L + t);
+          if (P.modulate) x *= (expf(-tpos * fabsf(__ldg(P.deltas + c))) + P.shift);
+          dh[(size_t)c * P.L + t] = x;
+        }
+        a[j] = x;
+      }
+      store_row_split<16>(smem, row, part * 16, a);        // the previous MMA group has completed (waited below)
+      cp_async_wait_all();
+      fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        fence_after_sync();
+        const uint32_t sb = sbase + kOffW3hi + (q & 1) * 32768;
+        const uint32_t idesc = make_idesc(64);
+        uint32_t acc = q > 0 ? 1u : 0u;
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t aa = sbase + ((pass == 1) ? kOffAlo : kOffAhi);
+          const uint32_t bb = sb + ((pass == 2) ? 16384u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            mma_tf32(tmem, make_desc(aa + ks * 2 * kLBO), make_desc(bb + ks * 2 * kLBO), idesc, acc);
+            acc = 1;
+          }
+        }
+        mma_commit(mbar);
+      }
+      mbar_wait(mbar, phase); phase ^= 1;
+      fence_after_sync();
+      stream_item(smem, wimg, q + 2, tid);                  // refill the buffer this group just released
+    }
+
+    // ---- layer 3 -> 2 -> 1 backward through the sine activations
+    float X[16], da[16];
+    tmem_ld16(lane_addr + part * 16, da);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float sn, cs;
+      sincosf(fr[j] * pre3[j], &sn, &cs);
+      const float g = da[j] * cs;
+      X[j] = g * pre3[j];
+      a[j] = g * fr[j];
+    }
+    if (tv) store16(out + 5 * arr, a);
+    store_row_split<16>(smem, row, part * 16, a);
+    cp_async_wait_all();
+    fence_before_sync();
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {                                          // da2 = dp3 W2   (B = W2^T image, item nq)
+      fence_after_sync();
+      const uint32_t sb = sbase + kOffW3hi + (nq & 1) * 32768;
+      issue_layer(tmem, sbase + kOffAhi, sbase + kOffAlo, sb, sb + 16384u, 64, mbar);
+    }
+    mbar_wait(mbar, phase); phase ^= 1;
+    fence_after_sync();
+    tmem_ld16(lane_addr + part * 16, da);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float sn, cs;
+      sincosf(fr[j] * pre2[j], &sn, &cs);
+      const float g = da[j] * cs;
+      X[j] = fmaf(g, pre2[j], X[j]);
+      a[j] = g * fr[j];
+    }
+    if (tv) store16(out + 4 * arr, a);
+    store_row_split<16>(smem, row, part * 16, a);
+    fence_before_sync();
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {                                          // da1 = dp2 W1   (B = W1^T image, item nq+1)
+      fence_after_sync();
+      const uint32_t sb = sbase + kOffW3hi + ((nq + 1) & 1) * 32768;
+      issue_layer(tmem, sbase + kOffAhi, sbase + kOffAlo, sb, sb + 16384u, 64, mbar);
+    }
+    mbar_wait(mbar, phase); phase ^= 1;
+    fence_after_sync();
+    tmem_ld16(lane_addr + part * 16, da);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float sn, cs;
+      sincosf(fr[j] * pre1[j], &sn, &cs);
+      const float g = da[j] * cs;
+      X[j] = fmaf(g, pre1[j], X[j]);
+      a[j] = g * fr[j];
+    }
+    if (tv) { store16(out + 3 * arr, a); store16(out + 6 * arr, X); }
+    fence_before_sync();
+    __syncthreads();
+  }
+
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+  }
+}
+
 }  // namespace tc
 }  // namespace hy

@@ -2,7 +2,30 @@
 #include "filter_tc.cuh"
 namespace hy {
 
-size_t filter_tc_wimg_bytes(int D) { return tc::wimg_floats(D) * sizeof(float); }
+size_t filter_tc_wimg_bytes(int D) {
+  const size_t a = tc::wimg_floats(D), b = tc::wimg_bwd_floats(D);
+  return (a > b ? a : b) * sizeof(float);
+}
+
+cudaError_t launch_filter_bwd_tc(const FilterParams& P, float* wimg, const float* dk, float* dh, float* scratch,
+                                 cudaStream_t s) {
+  cudaError_t e = set_smem(tc::filter_tc_bwd_kernel, tc::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  prof_begin(K_FILTER_TC_PREP, s);
+  tc::filter_tc_prep_bwd_kernel<<<64, 256, 0, s>>>(P.W1, P.W2, P.W3, P.D, wimg);
+  prof_end(K_FILTER_TC_PREP, s);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int ntiles = (P.L + tc::kTileM - 1) / tc::kTileM;
+  const int grid = ntiles < sms ? ntiles : sms;
+  prof_begin(K_FILTER_TC_BWD, s);
+  tc::filter_tc_bwd_kernel<<<grid, tc::kThreads, tc::kSmemBytes, s>>>(P, wimg, dk, dh, scratch, ntiles);
+  prof_end(K_FILTER_TC_BWD, s);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_filter_fwd_tc(const FilterParams& P, float* wimg, float* kout, cudaStream_t s) {
   cudaError_t e = set_smem(tc::filter_tc_fwd_kernel, tc::kSmemBytes);

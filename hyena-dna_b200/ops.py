@@ -72,8 +72,41 @@ def filter_forward(z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, shift, modula
     return k
 
 
+def _filter_backward_tc(z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, shift, modulate, L, dk, need_dz):
+    """Tensor-core backward: stage 1 on tcgen05 (csrc/filter_tc.cuh), stage 2 = sequence-length reductions."""
+    zz, tt, E, N, D = _filter_args(z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, shift, modulate, L)
+    ws = [x.contiguous() for x in (W0, b0, W1, b1, W2, b2, W3)]
+    fr = freq.reshape(-1).contiguous()
+    dl = deltas.reshape(-1).contiguous()
+    dk = dk.contiguous()
+    dev = z.device
+    dh = torch.empty(D, L, dtype=torch.float32, device=dev)
+    sc = torch.empty(7, L, 64, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().hyena_b200_filter_bwd_stage1(
+            _ptr(zz), zz.stride(0), _ptr(tt), *[_ptr(w) for w in ws], _ptr(fr), _ptr(dl),
+            float(shift), int(bool(modulate)), int(L), E, N, D, _ptr(dk), _ptr(dh), _ptr(sc), _stream()))
+    a1, a2, a3, dp1, dp2, dp3, X = sc.unbind(0)
+    if gemm_mode() == "bf16x9":
+        dW3 = torch.empty(D, 64, dtype=torch.float32, device=dev)
+        # dW3^T (64 x D, ld 64) = a3^T (64 x L, stored, op N) dh^T (L x D, stored ld L, op N)
+        gemm(0, 0, 64, D, L, a3, 64, 0, dh, L, 0, dW3, 64, 0)
+    else:
+        dW3 = dh @ a3
+    dW2 = dp3.t() @ a2
+    dW1 = dp2.t() @ a1
+    dW0 = dp1.t() @ zz
+    grads = [dW0, dp1.sum(0), dW1, dp2.sum(0), dW2, dp3.sum(0), dW3]
+    dfreq = X.sum(0)
+    dz = (dp1 @ ws[0]) if need_dz else None
+    return grads, dfreq, dz
+
+
 def filter_backward(z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, shift, modulate, L, dk, need_dz):
     _need_cuda(z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, dk)
+    import os
+    if os.environ.get("HYENA_B200_FILTER", "tc") != "simt":
+        return _filter_backward_tc(z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, shift, modulate, L, dk, need_dz)
     zz, tt, E, N, D = _filter_args(z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, shift, modulate, L)
     ws = [x.contiguous() for x in (W0, b0, W1, b1, W2, b2, W3)]
     fr = freq.reshape(-1).contiguous()
