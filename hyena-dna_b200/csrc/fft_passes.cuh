@@ -93,6 +93,9 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, boo
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // rows [row0, row0+nrows) x columns [colbase, colbase+C) of the packed row `prow` (L floats), with a 4-float
 // halo on the left (the 3-tap filter reaches back two samples).  dst pitch: 2C+4 floats.
@@ -192,9 +195,13 @@ struct ColGeo {
   // staged four slots (4*R2 rows) at a time with up to five tensors
   static constexpr int DATA_ROWS = M1 >= 2 ? M1 / 2 : 1;
   static constexpr int WP = 2 * C + 4, XP = 2 * C;               // staged row pitches (floats): with / without halo
-  static constexpr int BATCH_ROWS = 4 * R2;
+  // inverse epilogue: double-buffered batches of SB slots (SB*R2 consecutive rows): 4 slots for the forward
+  // epilogue (three windowed tensors), 2 for the backward one (three windowed + two plain tensors)
+  static constexpr int SB_FWD = 4, SB_BWD = 2;
   static constexpr size_t STAGE_FWD = TWO ? (size_t)DATA_ROWS * (WP + WP) * sizeof(float) : 0;
-  static constexpr size_t STAGE_INV = TWO ? (size_t)BATCH_ROWS * (3 * WP + 2 * XP) * sizeof(float) : 0;
+  static constexpr size_t BATCH_FWD_FLOATS = (size_t)SB_FWD * R2 * (3 * WP);
+  static constexpr size_t BATCH_BWD_FLOATS = (size_t)SB_BWD * R2 * (3 * WP + 2 * XP);
+  static constexpr size_t STAGE_INV = TWO ? 2 * (BATCH_FWD_FLOATS > BATCH_BWD_FLOATS ? BATCH_FWD_FLOATS : BATCH_BWD_FLOATS) * sizeof(float) : 0;
   static constexpr size_t SMEM_FWD = EXCH > STAGE_FWD ? EXCH : STAGE_FWD;
   static constexpr size_t SMEM_INV = EXCH > STAGE_INV ? EXCH : STAGE_INV;
   static constexpr size_t SMEM = EXCH;
@@ -451,33 +458,51 @@ col_inv_kernel(const PassArgs a) {
     block_fft<CG::TWO ? LOGM1 : 5, true, false>(v, smem + col * CG::PITCH, q, a.T.tw1024, CtaSync{});
     // only m1 < M1/2 (slots s < 16) can hold samples t < L
     if ((MODE == INV_CONV_FWD || MODE == INV_BWD_DG) && a.stage) {
-      // epilogue operands staged through shared memory four slots (4*R2 consecutive rows) at a time
+      // epilogue operands staged through shared memory, SB slots (SB*R2 consecutive rows) per batch, double
+      // buffered: the cp.async group of batch k+1 is in flight while batch k is consumed
+      constexpr int SB = (MODE == INV_BWD_DG) ? CG::SB_BWD : CG::SB_FWD;
+      constexpr int NBATCH = 16 / SB;
+      constexpr int BROWS = SB * CG::R2;
+      constexpr size_t BFLOATS = (MODE == INV_BWD_DG) ? CG::BATCH_BWD_FLOATS : CG::BATCH_FWD_FLOATS;
       float* st = reinterpret_cast<float*>(smem_raw);
-      float* w0 = st;
-      float* w1 = w0 + CG::BATCH_ROWS * CG::WP;
-      float* w2 = w1 + CG::BATCH_ROWS * CG::WP;
-      float* x0 = w2 + CG::BATCH_ROWS * CG::WP;
-      float* x1 = x0 + CG::BATCH_ROWS * CG::XP;
-      static_for<0, 4>([&](auto g_) {
-        constexpr int s0 = decltype(g_)::value * 4;
-        const int row0 = CG::R2 * s0;
-        __syncthreads();                                // previous users of the area (FFT exchange / last batch) are done
-        stage_windows<CG::C, kM2>(w0, a.p + row_off(b, c, 3 * a.D, L), row0, CG::BATCH_ROWS, colbase, L);
-        stage_windows<CG::C, kM2>(w1, a.p + row_off(b, a.D + c, 3 * a.D, L), row0, CG::BATCH_ROWS, colbase, L);
-        stage_windows<CG::C, kM2>(w2, a.p + row_off(b, 2 * a.D + c, 3 * a.D, L), row0, CG::BATCH_ROWS, colbase, L);
+      const float* p0 = a.p + row_off(b, c, 3 * a.D, L);
+      const float* p1 = a.p + row_off(b, a.D + c, 3 * a.D, L);
+      const float* p2 = a.p + row_off(b, 2 * a.D + c, 3 * a.D, L);
+      auto issue = [&](int k) {
+        float* w0 = st + (size_t)(k & 1) * BFLOATS;
+        float* w1 = w0 + BROWS * CG::WP;
+        float* w2 = w1 + BROWS * CG::WP;
+        const int row0 = BROWS * k;
+        stage_windows<CG::C, kM2>(w0, p0, row0, BROWS, colbase, L);
+        stage_windows<CG::C, kM2>(w1, p1, row0, BROWS, colbase, L);
+        stage_windows<CG::C, kM2>(w2, p2, row0, BROWS, colbase, L);
         if constexpr (MODE == INV_BWD_DG) {
-          stage_plain<CG::C, kM2>(x0, a.src + row_off(b, c, a.D, L), row0, CG::BATCH_ROWS, colbase, L);
-          stage_plain<CG::C, kM2>(x1, a.src2 + row_off(b, c, a.D, L), row0, CG::BATCH_ROWS, colbase, L);
+          float* x0 = w2 + BROWS * CG::WP;
+          float* x1 = x0 + BROWS * CG::XP;
+          stage_plain<CG::C, kM2>(x0, a.src + row_off(b, c, a.D, L), row0, BROWS, colbase, L);
+          stage_plain<CG::C, kM2>(x1, a.src2 + row_off(b, c, a.D, L), row0, BROWS, colbase, L);
         }
-        cp_async_wait_all();
+        cp_async_commit();
+      };
+      __syncthreads();                                  // the FFT exchange area is free
+      issue(0);
+      static_for<0, NBATCH>([&](auto g_) {
+        constexpr int k = decltype(g_)::value;
+        if constexpr (k + 1 < NBATCH) { issue(k + 1); cp_async_wait_group<1>(); } else { cp_async_wait_group<0>(); }
         __syncthreads();
-        static_for<0, 4>([&](auto j_) {
+        const float* w0 = st + (size_t)(k & 1) * BFLOATS;
+        const float* w1 = w0 + BROWS * CG::WP;
+        const float* w2 = w1 + BROWS * CG::WP;
+        const float* x0 = w2 + BROWS * CG::WP;
+        const float* x1 = x0 + BROWS * CG::XP;
+        static_for<0, SB>([&](auto j_) {
           constexpr int j = decltype(j_)::value;
-          const int m1 = CG::R2 * (s0 + j) + q;
+          constexpr int s = k * SB + j;
+          const int m1 = CG::R2 * s + q;
           const int t0 = 2 * (m1 * kM2 + m2);
           if (t0 < L) {
             InvIn in;
-            const int rr = m1 - row0;
+            const int rr = m1 - BROWS * k;
             staged_window<CG::C>(w0, rr, col, t0, cx.k0.ib, in.P0);
             staged_window<CG::C>(w1, rr, col, t0, cx.k1.ib, in.P1);
             staged_window<CG::C>(w2, rr, col, t0, cx.k2.ib, in.P2);
@@ -485,10 +510,11 @@ col_inv_kernel(const PassArgs a) {
               in.a = staged_pair<CG::C>(x0, rr, col);
               in.b = staged_pair<CG::C>(x1, rr, col);
             }
-            float2 y = v[Geo<CG::TWO ? LOGM1 : 5>::slot(s0 + j)];
+            float2 y = v[Geo<CG::TWO ? LOGM1 : 5>::slot(s)];
             inv_finish<MODE>(a, cx, b, c, t0, vec, make_float2(y.x * a.scale, y.y * a.scale), in);
           }
         });
+        if constexpr (k + 2 < NBATCH) __syncthreads();    // buffer k&1 is refilled by issue(k+2) next round
       });
     } else {
       // register path: slots are handled four at a time with all their loads issued before the first use

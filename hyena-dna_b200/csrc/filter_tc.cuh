@@ -481,13 +481,18 @@ filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const
 
     // ---- da3 = dh W3, 64 channels per MMA group; dh = dk * (exp(-t|delta|) + shift) also goes to HBM (stage 2 needs it)
     const float tpos = tv ? __ldg(P.t + t) : 0.f;
+    float nx[16];                                            // dk of the next chunk, loaded one MMA group ahead
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int c = part * 16 + j;
+      nx[j] = (c < P.D && tv) ? __ldg(dk + (size_t)c * P.L + t) : 0.f;
+    }
     for (int q = 0; q < nq; ++q) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int c = q * 64 + part * 16 + j;
-        float x = 0.f;
+        float x = nx[j];
         if (c < P.D && tv) {
-          x = __ldg(dk + (size_t)c * P.L + t);
           if (P.modulate) x *= (expf(-tpos * fabsf(__ldg(P.deltas + c))) + P.shift);
           dh[(size_t)c * P.L + t] = x;
         }
@@ -513,6 +518,13 @@ filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const
           }
         }
         mma_commit(mbar);
+      }
+      if (q + 1 < nq) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int c = (q + 1) * 64 + part * 16 + j;
+          nx[j] = (c < P.D && tv) ? __ldg(dk + (size_t)c * P.L + t) : 0.f;
+        }
       }
       mbar_wait(mbar, phase); phase ^= 1;
       fence_after_sync();

@@ -89,12 +89,17 @@ def _filter_backward_tc(z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, shift, m
     a1, a2, a3, dp1, dp2, dp3, X = sc.unbind(0)
     if gemm_mode() == "bf16x9":
         dW3 = torch.empty(D, 64, dtype=torch.float32, device=dev)
+        dW2 = torch.empty(64, 64, dtype=torch.float32, device=dev)
+        dW1 = torch.empty(64, 64, dtype=torch.float32, device=dev)
         # dW3^T (64 x D, ld 64) = a3^T (64 x L, stored, op N) dh^T (L x D, stored ld L, op N)
         gemm(0, 0, 64, D, L, a3, 64, 0, dh, L, 0, dW3, 64, 0)
+        # dW2^T (64 j x 64 i, ld 64) = a2^T (64 x L, stored, op N) dp3 (L x 64; stored as (64 x L) -> op T)
+        gemm(0, 1, 64, 64, L, a2, 64, 0, dp3, 64, 0, dW2, 64, 0)
+        gemm(0, 1, 64, 64, L, a1, 64, 0, dp2, 64, 0, dW1, 64, 0)
     else:
         dW3 = dh @ a3
-    dW2 = dp3.t() @ a2
-    dW1 = dp2.t() @ a1
+        dW2 = dp3.t() @ a2
+        dW1 = dp2.t() @ a1
     dW0 = dp1.t() @ zz
     grads = [dW0, dp1.sum(0), dW1, dp2.sum(0), dW2, dp3.sum(0), dW3]
     dfreq = X.sum(0)
