@@ -197,11 +197,13 @@ struct ColGeo {
   static constexpr int WP = 2 * C + 4, XP = 2 * C;               // staged row pitches (floats): with / without halo
   // inverse epilogue: double-buffered batches of SB slots (SB*R2 consecutive rows): 4 slots for the forward
   // epilogue (three windowed tensors), 2 for the backward one (three windowed + two plain tensors)
-  static constexpr int SB_FWD = 4, SB_BWD = 2;
+  static constexpr int SB_FWD = 4, SB_BWD = 4;
   static constexpr size_t STAGE_FWD = TWO ? (size_t)DATA_ROWS * (WP + WP) * sizeof(float) : 0;
   static constexpr size_t BATCH_FWD_FLOATS = (size_t)SB_FWD * R2 * (3 * WP);
   static constexpr size_t BATCH_BWD_FLOATS = (size_t)SB_BWD * R2 * (3 * WP + 2 * XP);
-  static constexpr size_t STAGE_INV = TWO ? 2 * (BATCH_FWD_FLOATS > BATCH_BWD_FLOATS ? BATCH_FWD_FLOATS : BATCH_BWD_FLOATS) * sizeof(float) : 0;
+  // the forward epilogue is double buffered, the (larger) backward batches are not (measured: 8 half-size
+  // double-buffered batches were 2x slower than 4 full-size single-buffered ones)
+  static constexpr size_t STAGE_INV = TWO ? (2 * BATCH_FWD_FLOATS > BATCH_BWD_FLOATS ? 2 * BATCH_FWD_FLOATS : BATCH_BWD_FLOATS) * sizeof(float) : 0;
   static constexpr size_t SMEM_FWD = EXCH > STAGE_FWD ? EXCH : STAGE_FWD;
   static constexpr size_t SMEM_INV = EXCH > STAGE_INV ? EXCH : STAGE_INV;
   static constexpr size_t SMEM = EXCH;
@@ -458,8 +460,9 @@ col_inv_kernel(const PassArgs a) {
     block_fft<CG::TWO ? LOGM1 : 5, true, false>(v, smem + col * CG::PITCH, q, a.T.tw1024, CtaSync{});
     // only m1 < M1/2 (slots s < 16) can hold samples t < L
     if ((MODE == INV_CONV_FWD || MODE == INV_BWD_DG) && a.stage) {
-      // epilogue operands staged through shared memory, SB slots (SB*R2 consecutive rows) per batch, double
-      // buffered: the cp.async group of batch k+1 is in flight while batch k is consumed
+      // epilogue operands staged through shared memory, SB slots (SB*R2 consecutive rows) per batch; forward:
+      // double buffered, the cp.async group of batch k+1 is in flight while batch k is consumed
+      constexpr bool DBL = (MODE == INV_CONV_FWD);
       constexpr int SB = (MODE == INV_BWD_DG) ? CG::SB_BWD : CG::SB_FWD;
       constexpr int NBATCH = 16 / SB;
       constexpr int BROWS = SB * CG::R2;
@@ -469,7 +472,7 @@ col_inv_kernel(const PassArgs a) {
       const float* p1 = a.p + row_off(b, a.D + c, 3 * a.D, L);
       const float* p2 = a.p + row_off(b, 2 * a.D + c, 3 * a.D, L);
       auto issue = [&](int k) {
-        float* w0 = st + (size_t)(k & 1) * BFLOATS;
+        float* w0 = st + (size_t)(DBL ? (k & 1) : 0) * BFLOATS;
         float* w1 = w0 + BROWS * CG::WP;
         float* w2 = w1 + BROWS * CG::WP;
         const int row0 = BROWS * k;
@@ -485,12 +488,17 @@ col_inv_kernel(const PassArgs a) {
         cp_async_commit();
       };
       __syncthreads();                                  // the FFT exchange area is free
-      issue(0);
+      if constexpr (DBL) issue(0);
       static_for<0, NBATCH>([&](auto g_) {
         constexpr int k = decltype(g_)::value;
-        if constexpr (k + 1 < NBATCH) { issue(k + 1); cp_async_wait_group<1>(); } else { cp_async_wait_group<0>(); }
+        if constexpr (DBL) {
+          if constexpr (k + 1 < NBATCH) { issue(k + 1); cp_async_wait_group<1>(); } else { cp_async_wait_group<0>(); }
+        } else {
+          issue(k);
+          cp_async_wait_group<0>();
+        }
         __syncthreads();
-        const float* w0 = st + (size_t)(k & 1) * BFLOATS;
+        const float* w0 = st + (size_t)(DBL ? (k & 1) : 0) * BFLOATS;
         const float* w1 = w0 + BROWS * CG::WP;
         const float* w2 = w1 + BROWS * CG::WP;
         const float* x0 = w2 + BROWS * CG::WP;
@@ -514,7 +522,7 @@ col_inv_kernel(const PassArgs a) {
             inv_finish<MODE>(a, cx, b, c, t0, vec, make_float2(y.x * a.scale, y.y * a.scale), in);
           }
         });
-        if constexpr (k + 2 < NBATCH) __syncthreads();    // buffer k&1 is refilled by issue(k+2) next round
+        if constexpr (DBL ? (k + 2 < NBATCH) : (k + 1 < NBATCH)) __syncthreads();   // the buffer is refilled next round
       });
     } else {
       // register path: slots are handled four at a time with all their loads issued before the first use
