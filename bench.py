@@ -40,13 +40,16 @@ METRIC = "nucleotides/sec through HyenaOperator fwd+bwd at L=1M d=256"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seqlen", type=int, default=L_FULL, help="override L (debug only; invalidates the number)")
     ap.add_argument("--d-model", type=int, default=D_MODEL)
     ap.add_argument("--batch", type=int, default=1, help="samples per GPU")
-    ap.add_argument("--cpu-sample-len", type=int, default=1 << 16,
+    ap.add_argument("--cpu-threads", type=int, default=0,
+                    help="host threads for the CPU arm (0 = min(cores, 16): torch CPU ops were ~40x SLOWER with all "
+                         "128 hardware threads of the B200 host than the survey box was with 8)")
+    ap.add_argument("--cpu-sample-len", type=int, default=1 << 17,
                     help="sequence length of the bounded CPU sample (cpu_baseline / reference arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -55,7 +58,7 @@ def parse():
 
 # ----------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -65,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -75,10 +78,14 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def mark(self):
+        """wall-clock marker: samples between two marks are the ones taken under load"""
+        return time.time()
+
+    def stop(self, t_begin=None, t_end=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -86,10 +93,18 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        import datetime
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
+            try:
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if t_begin is not None and not (t_begin - 0.05 <= ts <= t_end + 0.05):
+                    continue
+            except ValueError:
+                pass
+            f = f[1:]
             try:
                 sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
             except ValueError:
@@ -103,21 +118,26 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_run(L, D, B, steps, warmup):
-    """Time the oracle (reference torch.fft path restated, fp32, all host threads) on CPU."""
+def cpu_reference_run(L, D, B, steps, warmup, threads=0):
+    """Time the oracle (reference torch.fft path restated, fp32) on the host cores."""
     from oracle import hyena_oracle as O
-    cores = os.cpu_count() or 1
+    cores = threads if threads > 0 else min(os.cpu_count() or 1, 16)
     torch.set_num_threads(cores)
     g = torch.Generator().manual_seed(0)
     P = O.init_params(D, L, emb_dim=EMB, w=W_FREQ, generator=g, init_std=0.02)
     u, _ = O.nucleotide_activations(B, L, D)
     dy = torch.randn(B, L, D, generator=g)
+    tw = time.perf_counter()
     for _ in range(warmup):
         O.operator_fwd_bwd(u, P, dy)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        O.operator_fwd_bwd(u, P, dy)
-    dt = (time.perf_counter() - t0) / max(steps, 1)
+    tw = (time.perf_counter() - tw) / max(warmup, 1)
+    if warmup and tw > 30.0:          # pathologically slow host: do not burn minutes, report the warm-up step
+        steps, dt = 0, tw
+    else:
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.operator_fwd_bwd(u, P, dy)
+        dt = (time.perf_counter() - t0) / max(steps, 1)
     return {"value": B * L / dt, "unit": "nt/s", "cores": cores, "kind": "port",
             "sample": f"oracle fwd+bwd, fp32 torch CPU, B={B} L={L} D={D}, {steps} step(s) after {warmup} warm-up "
                       f"({dt:.2f} s/step)"}, dt
@@ -128,7 +148,7 @@ def reference_arm(args):
     if rank != 0:
         return
     Ls = min(args.cpu_sample_len, args.seqlen)
-    cb, dt = cpu_reference_run(Ls, args.d_model, 1, args.steps, min(args.warmup, 1))
+    cb, dt = cpu_reference_run(Ls, args.d_model, 1, args.steps, min(args.warmup, 1), args.cpu_threads)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "nt/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -192,6 +212,9 @@ def main():
             H.distributed.allreduce_grads(params)
         return y
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()              # running through warm-up so that samples exist when the timed region starts
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
@@ -201,22 +224,22 @@ def main():
             dist.barrier()
 
     # ---------------- timed region (device-resident inputs)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     n0 = H.launch_count()
     H._lib.profile_begin()
     barrier(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = sampler.mark()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
-    torch.cuda.synchronize(); barrier()
+    torch.cuda.synchronize()
+    t_end = sampler.mark()
+    barrier()
     ms = e0.elapsed_time(e1)
     prof = H._lib.profile_end()
     launches = H.launch_count() - n0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -301,7 +324,7 @@ def main():
     # ---------------- CPU baseline (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu, _ = cpu_reference_run(min(args.cpu_sample_len, L), D, 1, 1, 1)
+        cpu, _ = cpu_reference_run(min(args.cpu_sample_len, L), D, 1, 1, 1, args.cpu_threads)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "nt/s", "n_gpus": world, "steps": args.steps,
