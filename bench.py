@@ -30,6 +30,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: keep NCCL's own banner ("NCCL version ...", printed to stdout when the
+# environment sets NCCL_DEBUG) on stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import torch  # noqa: E402
 
