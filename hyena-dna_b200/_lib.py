@@ -35,8 +35,8 @@ SIGNATURES = {
                               + [c_fp] * 8 + [c_fp, _i, _vp]),
     "hyena_b200_filter_bwd_stage1": (_i, [c_fp, _i, c_fp] + [c_fp] * 7 + [c_fp, c_fp, _f, _i, _i, _i, _i, _i, c_fp, c_fp, c_fp, _vp]),
     "hyena_b200_filter_spectrum": (_i, [c_fp, c_fp, _i, _i, _vp, _sz, _vp]),
-    "hyena_b200_core_fwd": (_i, [c_fp] * 8 + [_i, _i, _i, _vp, _sz, _vp]),
-    "hyena_b200_core_bwd": (_i, [c_fp] * 15 + [_i, _i, _i, _vp, _sz, _vp]),
+    "hyena_b200_core_fwd": (_i, [c_fp] * 9 + [_i, _i, _i, _vp, _sz, _vp]),
+    "hyena_b200_core_bwd": (_i, [c_fp] * 16 + [_i, _i, _i, _vp, _sz, _vp]),
     "hyena_b200_fftconv_fwd": (_i, [c_fp] * 4 + [_i, _i, _i, _vp, _sz, _vp]),
     "hyena_b200_fftconv_bwd": (_i, [c_fp] * 7 + [_i, _i, _i, _vp, _sz, _vp]),
     "hyena_b200_gemm_available": (_i, []),

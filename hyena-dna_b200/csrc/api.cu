@@ -117,7 +117,7 @@ static size_t group_budget_bytes() {
   static size_t v = 0;
   if (!v) {
     const char* e = getenv("HYENA_B200_GROUP_MB");
-    long mb = e ? atol(e) : 256;
+    long mb = e ? atol(e) : 512;
     if (mb < 1) mb = 1;
     v = (size_t)mb << 20;
   }
@@ -335,8 +335,8 @@ HY_API int hyena_b200_filter_spectrum(const float* k, float* kspec, int D, int L
 }
 
 HY_API int hyena_b200_core_fwd(const float* p, const float* in_bias, const float* sw, const float* sb, const float* kspec,
-                        const float* fbias, float* y_pre, float* c_save, int B, int D, int L, void* workspace,
-                        size_t workspace_bytes, void* stream) {
+                        const float* fbias, float* y_pre, float* c_save, float* gspec_save, int B, int D, int L,
+                        void* workspace, size_t workspace_bytes, void* stream) {
   if (check_shape(B, D, L)) return 1;
   HY_CHECK(p && sw && sb && kspec && fbias && y_pre, "null pointer");
   cudaStream_t s = (cudaStream_t)stream;
@@ -347,6 +347,7 @@ HY_API int hyena_b200_core_fwd(const float* p, const float* in_bias, const float
   PassArgs a = base_args(B, D, L, T);
   a.A = c.A; a.kspec = reinterpret_cast<const float2*>(kspec);
   a.p = p; a.in_bias = in_bias; a.sw = sw; a.sb = sb; a.fbias = fbias; a.out = y_pre; a.out2 = c_save;
+  a.gspec = reinterpret_cast<float2*>(gspec_save);
   a.vec = ((L & 1) == 0) && aligned8(p) && aligned8(y_pre) && (!c_save || aligned8(c_save));
   a.stage = ((L & 3) == 0) && aligned16(p) && !getenv("HYENA_B200_NO_STAGE");
   for (int c0 = 0; c0 < D; c0 += c.nch) {
@@ -360,9 +361,9 @@ HY_API int hyena_b200_core_fwd(const float* p, const float* in_bias, const float
 }
 
 HY_API int hyena_b200_core_bwd(const float* dy_pre, const float* p, const float* in_bias, const float* sw, const float* sb,
-                        const float* kspec, const float* fbias, const float* c_saved, float* dp, float* dk,
-                        float* dsw, float* dsb, float* dfbias, float* d_in_bias, float* ds_scratch, int B, int D,
-                        int L, void* workspace, size_t workspace_bytes, void* stream) {
+                        const float* kspec, const float* fbias, const float* c_saved, const float* gspec_saved,
+                        float* dp, float* dk, float* dsw, float* dsb, float* dfbias, float* d_in_bias,
+                        float* ds_scratch, int B, int D, int L, void* workspace, size_t workspace_bytes, void* stream) {
   if (check_shape(B, D, L)) return 1;
   HY_CHECK(dy_pre && p && sw && sb && kspec && fbias && c_saved && dp && dk && dsw && dsb && dfbias && ds_scratch,
            "null pointer");
@@ -383,8 +384,11 @@ HY_API int hyena_b200_core_bwd(const float* dy_pre, const float* p, const float*
     a.A2 = c.A2; a.A3 = c.A3;
     a.A = c.A; a.src = dy_pre;
     HY_CUDA(launch_col_fwd(COL_DC, a, n * B, s));        // A  <- columns of dc = dy_pre * x0
-    a.A = c.A2;
-    HY_CUDA(launch_col_fwd(COL_GATE, a, n * B, s));      // A2 <- columns of g = v * x1 (recomputed)
+    a.gspec = const_cast<float2*>(reinterpret_cast<const float2*>(gspec_saved));
+    if (!gspec_saved) {
+      a.A = c.A2;
+      HY_CUDA(launch_col_fwd(COL_GATE, a, n * B, s));    // A2 <- columns of g = v * x1 (recomputed)
+    }
     a.A = c.A;
     HY_CUDA(launch_row_pass(ROW_CONV_BWD, a, n, s));     // A <- rows of dg, A3 <- rows of dk
     a.src = dy_pre; a.src2 = c_saved; a.out2 = ds_scratch; a.red = dfbias;

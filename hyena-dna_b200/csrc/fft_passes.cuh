@@ -160,6 +160,7 @@ struct PassArgs {
   float2* A3;       // third scratch (bwd: per-channel dK' rows [ci][k1][m2])
   const float2* kspec;   // filter spectrum [c][k1][k2]
   float2* kspec_out;     // ROW_FILTER output
+  float2* gspec;         // ROW_CONV_FWD: optional output, spectrum of g per (b,c) row; ROW_CONV_BWD: optional input
   // tensors (see include/hyena_b200.h for layouts)
   const float* src;      // COL_FILTER: k (D,L); COL_PLAIN / INV_PLAIN_*: u (B,H,L); COL_DC & INV_BWD_DG: dy_pre (B,D,L)
   const float* src2;     // INV_PLAIN_BWD: dout (B,H,L); INV_BWD_DG: c_saved (B,D,L)
@@ -501,8 +502,8 @@ col_inv_kernel(const PassArgs a) {
         const float* w0 = st + (size_t)(DBL ? (k & 1) : 0) * BFLOATS;
         const float* w1 = w0 + BROWS * CG::WP;
         const float* w2 = w1 + BROWS * CG::WP;
-        const float* x0 = w2 + BROWS * CG::WP;
-        const float* x1 = x0 + BROWS * CG::XP;
+        [[maybe_unused]] const float* x0 = w2 + BROWS * CG::WP;
+        [[maybe_unused]] const float* x1 = x0 + BROWS * CG::XP;
         static_for<0, SB>([&](auto j_) {
           constexpr int j = decltype(j_)::value;
           constexpr int s = k * SB + j;
@@ -734,6 +735,10 @@ row_pass_kernel(const PassArgs a) {
       const float2* Krow = a.kspec + (size_t)c * rowElems + (size_t)id.k1 * M2;
       const float2* Kprow = a.kspec + (size_t)c * rowElems + (size_t)id.pk1 * M2;
       row_fft_to_smem<LOGM2>(Arow, ex, ex, q, a.T, rsync);
+      if (a.gspec) {                                    // keep the spectrum of g for the backward pass
+        float2* G = a.gspec + ((size_t)ci * a.B + (r - ci * a.B) + (size_t)a.c0 * a.B) * rowElems + (size_t)id.k1 * M2;
+        static_for<0, 32>([&](auto s_) { constexpr int s = decltype(s_)::value; G[TPR * s + q] = ex[TPR * s + q]; });
+      }
       __syncthreads();
       float2 v[32];
       static_for<0, 32>([&](auto s_) {
@@ -762,7 +767,12 @@ row_pass_kernel(const PassArgs a) {
         const float2* Grow = a.A2 + r * rowElems + (size_t)id.k1 * M2;
         row_fft_to_smem<LOGM2>(Drow, ex, zbuf, q, a.T, rsync);     // dc spectrum -> zbuf
         rsync();
-        row_fft_to_smem<LOGM2>(Grow, ex, ex, q, a.T, rsync);       // g spectrum  -> the exchange area itself
+        if (a.gspec) {                                             // saved by the forward pass: just load it
+          const float2* G = a.gspec + ((size_t)(a.c0 + ci) * a.B + b) * rowElems + (size_t)id.k1 * M2;
+          static_for<0, 32>([&](auto s_) { constexpr int s = decltype(s_)::value; ex[TPR * s + q] = __ldg(G + TPR * s + q); });
+        } else {
+          row_fft_to_smem<LOGM2>(Grow, ex, ex, q, a.T, rsync);     // g spectrum  -> the exchange area itself
+        }
         __syncthreads();
         float2 v[32];
         static_for<0, 32>([&](auto s_) {

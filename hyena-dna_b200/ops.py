@@ -100,9 +100,18 @@ def _filter_backward_tc(z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, shift, m
         dW3 = dh @ a3
         dW2 = dp3.t() @ a2
         dW1 = dp2.t() @ a1
-    dW0 = dp1.t() @ zz
-    grads = [dW0, dp1.sum(0), dW1, dp2.sum(0), dW2, dp3.sum(0), dW3]
-    dfreq = X.sum(0)
+    sums = sc[3:7].sum(dim=1)                       # one pass: colsum(dp1), colsum(dp2), colsum(dp3), colsum(X)
+    if gemm_mode() == "bf16x9":
+        zp = torch.zeros(L, 8, dtype=torch.float32, device=dev)
+        zp[:, :E] = zz
+        dW0p = torch.empty(64, 8, dtype=torch.float32, device=dev)
+        # dW0p^T (8 x 64, ld 8) = zp^T (8 x L, stored, op N) dp1 (L x 64; stored as (64 x L) -> op T)
+        gemm(0, 1, 8, 64, L, zp, 8, 0, dp1, 64, 0, dW0p, 8, 0)
+        dW0 = dW0p[:, :E].contiguous()
+    else:
+        dW0 = dp1.t() @ zz
+    grads = [dW0, sums[0], dW1, sums[1], dW2, sums[2], dW3]
+    dfreq = sums[3]
     dz = (dp1 @ ws[0]) if need_dz else None
     return grads, dfreq, dz
 
@@ -167,6 +176,11 @@ def filter_spectrum(k):
     return spec
 
 
+def _save_spectrum():
+    import os
+    return os.environ.get("HYENA_B200_SAVE_SPECTRUM", "1") != "0"
+
+
 def core_forward(p, in_bias, sw, sb, kspec, fbias, save_c):
     _need_cuda(p, in_bias, sw, sb, fbias)
     B, C3, L = p.shape
@@ -174,15 +188,18 @@ def core_forward(p, in_bias, sw, sb, kspec, fbias, save_c):
     assert p.is_contiguous() and kspec.is_contiguous()
     y = torch.empty(B, D, L, dtype=torch.float32, device=p.device)
     c = torch.empty(B, D, L, dtype=torch.float32, device=p.device) if save_c else None
+    # spectrum of the gated input, rows ordered (c, b): saves a column pass + a row FFT per row in backward
+    gs = (torch.empty(D * B, kspec.shape[-1], dtype=torch.complex64, device=p.device)
+          if (save_c and _save_spectrum()) else None)
     ws = workspace(B, D, L, False, p.device)
     with torch.cuda.device(p.device):
         _lib.check(_lib.lib().hyena_b200_core_fwd(
-            _ptr(p), _ptr(in_bias), _ptr(sw), _ptr(sb), _ptr(kspec), _ptr(fbias), _ptr(y), _ptr(c),
+            _ptr(p), _ptr(in_bias), _ptr(sw), _ptr(sb), _ptr(kspec), _ptr(fbias), _ptr(y), _ptr(c), _ptr(gs),
             B, D, L, _ptr(ws), ws.numel(), _stream()))
-    return y, c
+    return y, c, gs
 
 
-def core_backward(dy_pre, p, in_bias, sw, sb, kspec, fbias, c_saved):
+def core_backward(dy_pre, p, in_bias, sw, sb, kspec, fbias, c_saved, gspec=None):
     _need_cuda(dy_pre, p, in_bias, sw, sb, fbias, c_saved)
     B, C3, L = p.shape
     D = C3 // 3
@@ -199,7 +216,7 @@ def core_backward(dy_pre, p, in_bias, sw, sb, kspec, fbias, c_saved):
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().hyena_b200_core_bwd(
             _ptr(dy_pre), _ptr(p), _ptr(in_bias), _ptr(sw), _ptr(sb), _ptr(kspec), _ptr(fbias), _ptr(c_saved),
-            _ptr(dp), _ptr(dk), _ptr(dsw), _ptr(dsb), _ptr(dfb), _ptr(dib), _ptr(ds),
+            _ptr(gspec), _ptr(dp), _ptr(dk), _ptr(dsw), _ptr(dsb), _ptr(dfb), _ptr(dib), _ptr(ds),
             B, D, L, _ptr(ws), ws.numel(), _stream()))
     del ds
     return dp, dk, dsw, dsb, dfb, dib
@@ -216,15 +233,15 @@ class HyenaCoreFn(torch.autograd.Function):
         ib = in_bias.contiguous() if in_bias is not None else None
         kspec = filter_spectrum(k)
         need = any(ctx.needs_input_grad)
-        y, c = core_forward(p, ib, sw2, sb, kspec, fbias, need)
-        ctx.save_for_backward(p, ib, sw2, sb, kspec, fbias, c)
+        y, c, gs = core_forward(p, ib, sw2, sb, kspec, fbias, need)
+        ctx.save_for_backward(p, ib, sw2, sb, kspec, fbias, c, gs)
         ctx.sw_shape = sw.shape
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        p, ib, sw2, sb, kspec, fbias, c = ctx.saved_tensors
-        dp, dk, dsw, dsb, dfb, dib = core_backward(dy, p, ib, sw2, sb, kspec, fbias, c)
+        p, ib, sw2, sb, kspec, fbias, c, gs = ctx.saved_tensors
+        dp, dk, dsw, dsb, dfb, dib = core_backward(dy, p, ib, sw2, sb, kspec, fbias, c, gs)
         return dp, dib, dsw.reshape(ctx.sw_shape), dsb, dk, dfb
 
 

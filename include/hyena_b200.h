@@ -104,10 +104,12 @@ HY_API int hyena_b200_filter_spectrum(const float* k, float* kspec, int D, int L
  * (:404), gate v*x1 (:420), fftconv_ref with bias skip term (:59-88 via :261), gate *x0 (:432).
  *   sw (3D,3) = short_filter.weight[:,0,:], sb (3D) = short_filter.bias, in_bias (3D) = in_proj.bias
  *   or NULL, fbias (D) = filter_fn.bias.  c_save (B,D,L) receives the fftconv output (needed by
- *   core_bwd) when non-NULL. */
+ *   core_bwd) when non-NULL.  gspec_save ((D*B) rows of M complex64, row = c*B + b; may be NULL) receives the
+ *   packed spectrum of the gated input g = short(v)*short(x1); handing it back to core_bwd saves one column
+ *   pass and one row FFT per (b,c) row there (the reference saves u_f the same way, hyena.py:41). */
 HY_API int hyena_b200_core_fwd(const float* p, const float* in_bias, const float* sw, const float* sb,
                         const float* kspec, const float* fbias,
-                        float* y_pre, float* c_save, int B, int D, int L,
+                        float* y_pre, float* c_save, float* gspec_save, int B, int D, int L,
                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* backward of core_fwd (closed form: hyena.py:43-56 FFTConvFuncv2.backward,
@@ -116,6 +118,7 @@ HY_API int hyena_b200_core_fwd(const float* p, const float* in_bias, const float
  * ds_scratch (B,3D,L) is caller-provided scratch for the short-filter output grads. */
 HY_API int hyena_b200_core_bwd(const float* dy_pre, const float* p, const float* in_bias, const float* sw,
                         const float* sb, const float* kspec, const float* fbias, const float* c_saved,
+                        const float* gspec_saved /* from core_fwd, or NULL to recompute */,
                         float* dp, float* dk, float* dsw, float* dsb, float* dfbias, float* d_in_bias,
                         float* ds_scratch, int B, int D, int L,
                         void* workspace, size_t workspace_bytes, void* stream);
