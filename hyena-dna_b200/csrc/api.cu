@@ -391,12 +391,13 @@ HY_API int hyena_b200_core_bwd(const float* dy_pre, const float* p, const float*
     }
     a.A = c.A;
     HY_CUDA(launch_row_pass(ROW_CONV_BWD, a, n, s));     // A <- rows of dg, A3 <- rows of dk
-    a.src = dy_pre; a.src2 = c_saved; a.out2 = ds_scratch; a.red = dfbias;
+    a.src = dy_pre; a.src2 = c_saved; a.out2 = ds_scratch; a.red = dfbias; a.dsw = dsw; a.dsb = dsb;
     HY_CUDA(launch_col_inv(INV_BWD_DG, a, n * B, s));
     a.B = 1; a.out = dk;
     HY_CUDA(launch_col_inv(INV_DK, a, n, s));
   }
-  ShortBwdArgs sa{ds_scratch, p, in_bias, sw, dp, dsw, dsb, d_in_bias, L, 3 * D, a.vec};
+  // pass 3 already accumulated dsw / dsb from the operand windows it had staged: no second read of p here
+  ShortBwdArgs sa{ds_scratch, nullptr, in_bias, sw, dp, dsw, dsb, d_in_bias, L, 3 * D, a.vec};
   HY_CUDA(launch_short_bwd(sa, B, s));
   return 0;
 }

@@ -172,6 +172,8 @@ struct PassArgs {
   float* out;            // INV_CONV_FWD: y_pre (B,D,L); INV_DK: dk (D,L); INV_PLAIN_*: out/du (B,H,L)
   float* out2;           // INV_CONV_FWD: c_save (B,D,L) or null; INV_BWD_DG: dconv (B,3D,L)
   float* red;            // INV_BWD_DG: dfbias (D); INV_PLAIN_BWD: dD (H)   (atomicAdd)
+  float* dsw;            // INV_BWD_DG: d short_filter.weight (3D,3) (atomicAdd)
+  float* dsb;            // INV_BWD_DG: d short_filter.bias (3D)     (atomicAdd)
 };
 
 __device__ __forceinline__ size_t row_off(int b, int ch, int nch, int L) { return ((size_t)b * nch + ch) * (size_t)L; }
@@ -358,7 +360,17 @@ struct InvCtx {
   Taps k0, k1, k2;     // taps of x0, x1, v channels
   float fb;            // filter bias of this channel
   float red;           // per-thread partial of the reduction this mode produces
+  float rw[3][3];      // INV_BWD_DG: partials of d short_filter.weight for the x0 / x1 / v channels
+  float rb[3];         //             and of d short_filter.bias
 };
+
+// dw_j += ds[t0] P(t0-2+j) + ds[t0+1] P(t0-1+j);  db += ds[t0] + ds[t0+1]     (P = window of the filter input)
+__device__ __forceinline__ void tap_grads(float (&rw)[3], float& rb, const float2 ds, const float (&P)[4]) {
+  rw[0] = fmaf(ds.x, P[0], fmaf(ds.y, P[1], rw[0]));
+  rw[1] = fmaf(ds.x, P[1], fmaf(ds.y, P[2], rw[1]));
+  rw[2] = fmaf(ds.x, P[2], fmaf(ds.y, P[3], rw[2]));
+  rb += ds.x + ds.y;
+}
 
 // Everything pass 3 reads from HBM for one sample pair, loaded up front so that a batch of slots has all
 // its loads in flight before the first use (the epilogue is latency-bound otherwise).
@@ -411,9 +423,15 @@ __device__ __forceinline__ void inv_finish(const PassArgs& a, InvCtx& cx, int b,
     float2 dc = make_float2(dy.x * x0.x, dy.y * x0.y);
     float2 dg = make_float2(fmaf(dc.x, cx.fb, y.x), fmaf(dc.y, cx.fb, y.y));     // + bias * dc
     cx.red = fmaf(dc.x, x1.x * vv.x, fmaf(dc.y, x1.y * vv.y, cx.red));           // dbias += dc * g
-    store_pair(a.out2 + row_off(b, c, 3 * D, L), t0, L, vec, make_float2(dy.x * cs.x, dy.y * cs.y));           // d x0c
-    store_pair(a.out2 + row_off(b, D + c, 3 * D, L), t0, L, vec, make_float2(dg.x * vv.x, dg.y * vv.y));       // d x1c
-    store_pair(a.out2 + row_off(b, 2 * D + c, 3 * D, L), t0, L, vec, make_float2(dg.x * x1.x, dg.y * x1.y));   // d vc
+    const float2 d0 = make_float2(dy.x * cs.x, dy.y * cs.y);     // d short(x0)
+    const float2 d1 = make_float2(dg.x * vv.x, dg.y * vv.y);     // d short(x1)
+    const float2 d2 = make_float2(dg.x * x1.x, dg.y * x1.y);     // d short(v)
+    store_pair(a.out2 + row_off(b, c, 3 * D, L), t0, L, vec, d0);
+    store_pair(a.out2 + row_off(b, D + c, 3 * D, L), t0, L, vec, d1);
+    store_pair(a.out2 + row_off(b, 2 * D + c, 3 * D, L), t0, L, vec, d2);
+    tap_grads(cx.rw[0], cx.rb[0], d0, in.P0);                    // short-filter weight / bias grads, fused here so
+    tap_grads(cx.rw[1], cx.rb[1], d1, in.P1);                    // that short_conv_bwd need not re-read p
+    tap_grads(cx.rw[2], cx.rb[2], d2, in.P2);
   }
 }
 
@@ -432,7 +450,6 @@ col_inv_kernel(const PassArgs a) {
   constexpr int kM2 = CG::M2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* smem = reinterpret_cast<float2*>(smem_raw);
-  __shared__ float red_smem[8];
 
   const int r = blockIdx.y;
   const int ci = r / a.B, b = r - ci * a.B, c = a.c0 + ci;
@@ -567,15 +584,34 @@ col_inv_kernel(const PassArgs a) {
   }
 
   if constexpr (MODE == INV_BWD_DG || MODE == INV_PLAIN_BWD) {
-    float s = cx.red;
+    constexpr int NR = (MODE == INV_BWD_DG) ? 13 : 1;
+    __shared__ float red_all[8][NR];
+    float vals[NR];
+    vals[0] = cx.red;
+    if constexpr (MODE == INV_BWD_DG) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0) red_smem[threadIdx.x >> 5] = s;
+      for (int ch = 0; ch < 3; ++ch) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) vals[1 + 3 * ch + j] = cx.rw[ch][j];
+        vals[10 + ch] = cx.rb[ch];
+      }
+    }
     __syncthreads();
-    if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      float s = vals[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if ((threadIdx.x & 31) == 0) red_all[threadIdx.x >> 5][i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < NR) {
       float tot = 0.f;
-      for (int w = 0; w < (CG::THREADS + 31) / 32; ++w) tot += red_smem[w];
-      atomicAdd(a.red + c, tot);
+      for (int w = 0; w < (CG::THREADS + 31) / 32; ++w) tot += red_all[w][threadIdx.x];
+      const int i = threadIdx.x;
+      if (i == 0) atomicAdd(a.red + c, tot);
+      else if (i < 10) atomicAdd(a.dsw + 3 * (((i - 1) / 3) * a.D + c) + (i - 1) % 3, tot);
+      else atomicAdd(a.dsb + (i - 10) * a.D + c, tot);
     }
   }
 }

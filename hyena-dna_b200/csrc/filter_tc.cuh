@@ -52,6 +52,11 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = to_tf32(x - hi);
 }
 
+// Accurate sinf / sincosf are ~100 instructions each with their large-argument paths; inlined 48x per tile they made
+// the epilogue instruction-fetch bound (ncu: stall_no_instruction 5.1 per issue).  One out-of-line copy each.
+__device__ __noinline__ float sin_ni(float x) { return sinf(x); }
+__device__ __noinline__ float cos_ni(float x) { return cosf(x); }
+
 // ---------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -264,7 +269,7 @@ filter_tc_fwd_kernel(const FilterParams P, const float* __restrict__ wimg, float
         float acc = b0s[i];
 #pragma unroll
         for (int e = 0; e < kMaxE; ++e) acc = fmaf(W0s[i * 16 + e], z[e], acc);
-        a[j] = sinf(frs[i] * acc);
+        a[j] = sin_ni(frs[i] * acc);
       }
       store_row_split<16>(smem, row, part * 16, a);
     }
@@ -285,7 +290,7 @@ filter_tc_fwd_kernel(const FilterParams P, const float* __restrict__ wimg, float
       float a[16];
       tmem_ld16(lane_addr + part * 16, a);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) a[j] = sinf(frs[part * 16 + j] * (a[j] + bs[part * 16 + j]));
+      for (int j = 0; j < 16; ++j) a[j] = sin_ni(frs[part * 16 + j] * (a[j] + bs[part * 16 + j]));
       store_row_split<16>(smem, row, part * 16, a);        // the MMAs that read the A images have completed
       fence_before_sync();
       fence_async_smem();
@@ -446,7 +451,7 @@ filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const
 #pragma unroll
         for (int e = 0; e < kMaxE; ++e) acc = fmaf(W0s[i * 16 + e], z[e], acc);
         pre1[j] = acc;
-        a[j] = sinf(fr[j] * acc);
+        a[j] = sin_ni(fr[j] * acc);
       }
       store_row_split<16>(smem, row, part * 16, a);
       if (tv) store16(out + 0 * arr, a);
@@ -461,7 +466,7 @@ filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const
     fence_after_sync();
     tmem_ld16(lane_addr + part * 16, pre2);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { pre2[j] += b1s[part * 16 + j]; a[j] = sinf(fr[j] * pre2[j]); }
+    for (int j = 0; j < 16; ++j) { pre2[j] += b1s[part * 16 + j]; a[j] = sin_ni(fr[j] * pre2[j]); }
     store_row_split<16>(smem, row, part * 16, a);
     if (tv) store16(out + 1 * arr, a);
     fence_before_sync();
@@ -475,7 +480,7 @@ filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const
     fence_after_sync();
     tmem_ld16(lane_addr + part * 16, pre3);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { pre3[j] += b2s[part * 16 + j]; a[j] = sinf(fr[j] * pre3[j]); }
+    for (int j = 0; j < 16; ++j) { pre3[j] += b2s[part * 16 + j]; a[j] = sin_ni(fr[j] * pre3[j]); }
     if (tv) store16(out + 2 * arr, a);
     fence_before_sync();
 
@@ -536,8 +541,7 @@ filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const
     tmem_ld16(lane_addr + part * 16, da);
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      float sn, cs;
-      sincosf(fr[j] * pre3[j], &sn, &cs);
+      const float cs = cos_ni(fr[j] * pre3[j]);
       const float g = da[j] * cs;
       X[j] = g * pre3[j];
       a[j] = g * fr[j];
@@ -558,8 +562,7 @@ filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const
     tmem_ld16(lane_addr + part * 16, da);
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      float sn, cs;
-      sincosf(fr[j] * pre2[j], &sn, &cs);
+      const float cs = cos_ni(fr[j] * pre2[j]);
       const float g = da[j] * cs;
       X[j] = fmaf(g, pre2[j], X[j]);
       a[j] = g * fr[j];
@@ -579,8 +582,7 @@ filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const
     tmem_ld16(lane_addr + part * 16, da);
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      float sn, cs;
-      sincosf(fr[j] * pre1[j], &sn, &cs);
+      const float cs = cos_ni(fr[j] * pre1[j]);
       const float g = da[j] * cs;
       X[j] = fmaf(g, pre1[j], X[j]);
       a[j] = g * fr[j];

@@ -14,7 +14,7 @@ constexpr int kScSpan = 8192;     // positions per CTA
 
 struct ShortBwdArgs {
   const float* ds;      // (B,3D,L)
-  const float* p;       // (B,3D,L)
+  const float* p;       // (B,3D,L), or null when dsw / dsb were already accumulated by pass 3
   const float* in_bias; // (3D) or null
   const float* sw;      // (3D,3)
   float* dp;            // (B,3D,L)
@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) short_conv_bwd_kernel(const ShortBwdArgs 
   const int L = a.L;
   const bool vec = a.vec;
   const float* ds = a.ds + row_off(b, ch, a.C3, L);
-  const float* p = a.p + row_off(b, ch, a.C3, L);
+  const float* p = a.p ? a.p + row_off(b, ch, a.C3, L) : nullptr;
   float* dp = a.dp + row_off(b, ch, a.C3, L);
   const float w0 = __ldg(a.sw + 3 * ch), w1 = __ldg(a.sw + 3 * ch + 1), w2 = __ldg(a.sw + 3 * ch + 2);
   const float ib = a.in_bias ? __ldg(a.in_bias + ch) : 0.f;
@@ -40,16 +40,18 @@ __global__ void __launch_bounds__(256) short_conv_bwd_kernel(const ShortBwdArgs 
   for (int t0 = tbeg + 2 * threadIdx.x; t0 < tend; t0 += 512) {
     float2 d0 = load_pair(ds, t0, L, vec);
     float2 d1 = (t0 + 2 < L) ? load_pair(ds, t0 + 2, L, vec) : make_float2(0.f, 0.f);
-    float P[4];
-    load_window(p, t0, L, vec, ib, P);
     float2 o;
     o.x = fmaf(w2, d0.x, fmaf(w1, d0.y, w0 * d1.x));
     o.y = fmaf(w2, d0.y, fmaf(w1, d1.x, w0 * d1.y));
     store_pair(dp, t0, L, vec, o);
-    r[0] = fmaf(d0.x, P[0], fmaf(d0.y, P[1], r[0]));
-    r[1] = fmaf(d0.x, P[1], fmaf(d0.y, P[2], r[1]));
-    r[2] = fmaf(d0.x, P[2], fmaf(d0.y, P[3], r[2]));
-    r[3] += d0.x + d0.y;
+    if (a.p) {
+      float P[4];
+      load_window(p, t0, L, vec, ib, P);
+      r[0] = fmaf(d0.x, P[0], fmaf(d0.y, P[1], r[0]));
+      r[1] = fmaf(d0.x, P[1], fmaf(d0.y, P[2], r[1]));
+      r[2] = fmaf(d0.x, P[2], fmaf(d0.y, P[3], r[2]));
+      r[3] += d0.x + d0.y;
+    }
     r[4] += o.x + ((t0 + 1 < L) ? o.y : 0.f);
   }
   __shared__ float red[8][5];
@@ -64,8 +66,8 @@ __global__ void __launch_bounds__(256) short_conv_bwd_kernel(const ShortBwdArgs 
   if (threadIdx.x < 5) {
     float s = 0.f;
     for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-    if (threadIdx.x < 3) atomicAdd(a.dsw + 3 * ch + threadIdx.x, s);
-    else if (threadIdx.x == 3) atomicAdd(a.dsb + ch, s);
+    if (threadIdx.x < 3) { if (a.p) atomicAdd(a.dsw + 3 * ch + threadIdx.x, s); }
+    else if (threadIdx.x == 3) { if (a.p) atomicAdd(a.dsb + ch, s); }
     else if (a.dib) atomicAdd(a.dib + ch, s);
   }
 }
