@@ -275,36 +275,12 @@ def main():
         y_host = torch.empty(B, L, D).pin_memory()
         du_host = torch.empty(B, L, D).pin_memory()
         g_host = [torch.empty(p.shape).pin_memory() for p in params]
-        side = torch.cuda.Stream(device=dev)
-        main = torch.cuda.current_stream()
-        u_dev = torch.empty(B, L, D, device=dev)
-        dy_dev = torch.empty(B, L, D, device=dev)
+        hs = H.HostStep(op, B, L, chunks=4)
+
+        reduce_fn = H.distributed.allreduce_tensors if world > 1 else None
 
         def e2e_step():
-            for p in params:
-                p.grad = None
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                u_dev.copy_(u_host, non_blocking=True)
-                ev_u = torch.cuda.Event(); ev_u.record(side)
-                dy_dev.copy_(dy_host, non_blocking=True)          # overlaps the forward
-                ev_dy = torch.cuda.Event(); ev_dy.record(side)
-            main.wait_event(ev_u)
-            uu = u_dev.detach().requires_grad_(True)
-            y = op(uu)
-            ev_y = torch.cuda.Event(); ev_y.record(main)
-            with torch.cuda.stream(side):
-                side.wait_event(ev_y)
-                y_host.copy_(y.detach(), non_blocking=True)       # overlaps the backward
-            main.wait_event(ev_dy)
-            y.backward(dy_dev)
-            if world > 1:
-                H.distributed.allreduce_grads(params)
-            du_host.copy_(uu.grad, non_blocking=True)
-            for gh, p in zip(g_host, params):
-                gh.copy_(p.grad, non_blocking=True)
-            main.wait_stream(side)
-
+            hs.step(u_host, dy_host, y_host, du_host, g_host, reduce_fn)
         for _ in range(2):
             e2e_step()
         torch.cuda.synchronize(); barrier()
@@ -321,8 +297,9 @@ def main():
         pbytes = sum(p.numel() for p in params) * 4
         e2e = {"value": world * B * L / (e2e_ms * 1e-3), "unit": "nt/s", "ms_per_step": round(e2e_ms, 3),
                "h2d_bytes_per_step": 2 * B * L * D * 4, "d2h_bytes_per_step": 2 * B * L * D * 4 + pbytes,
-               "note": "per GPU; u,dy pinned host -> device; y, du, param grads device -> pinned host; "
-                       "dy upload overlaps forward, y download overlaps backward"}
+               "note": "per GPU, through hyena_dna_b200.HostStep: u,dy pinned host -> device; y, du, param grads device -> "
+                       "pinned host; u uploaded in 4 sequence chunks under the in_proj GEMM slices, dy under the forward, "
+                       "y and du downloaded in chunks under the backward"}
 
     # ---------------- CPU baseline (rank 0, N = 1 only)
     cpu = None

@@ -8,7 +8,8 @@ from .hyena import (ExponentialModulation, HyenaFilter, HyenaOperator, OptimModu
                     PositionalEmbedding, Sin)
 from .fftconv import FFTConvFunc, fftconv_bwd, fftconv_func, fftconv_fwd  # noqa: F401
 from . import distributed, ops, registry  # noqa: F401
+from .host import HostStep  # noqa: F401
 
 __all__ = ["HyenaOperator", "HyenaFilter", "PositionalEmbedding", "ExponentialModulation", "Sin", "OptimModule",
            "fftconv_func", "FFTConvFunc", "fftconv_fwd", "fftconv_bwd", "registry", "distributed", "ops",
-           "build", "launch_count", "HyenaB200Error", "LIB_PATH"]
+           "HostStep", "build", "launch_count", "HyenaB200Error", "LIB_PATH"]

@@ -41,6 +41,20 @@ def allreduce_grads(params, group=None, average=False):
     return flat.numel()
 
 
+def allreduce_tensors(tensors, group=None):
+    """In-place sum of a list of tensors across ranks with one flat all-reduce."""
+    if not tensors or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 0
+    flat = torch.cat([t.reshape(-1) for t in tensors])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for t in tensors:
+        n = t.numel()
+        t.copy_(flat[off:off + n].view_as(t))
+        off += n
+    return flat.numel()
+
+
 def gather_outputs(y, group=None):
     """All-gather batch shards of an output (verification / serving only: 1 GB per sample at L=1M)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
