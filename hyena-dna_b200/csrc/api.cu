@@ -390,7 +390,8 @@ HY_API int hyena_b200_core_bwd(const float* dy_pre, const float* p, const float*
       HY_CUDA(launch_col_fwd(COL_GATE, a, n * B, s));    // A2 <- columns of g = v * x1 (recomputed)
     }
     a.A = c.A;
-    HY_CUDA(launch_row_pass(ROW_CONV_BWD, a, n, s));     // A <- rows of dg, A3 <- rows of dk
+    static const bool bwd1 = !(getenv("HYENA_B200_ROW_BWD1") && !strcmp(getenv("HYENA_B200_ROW_BWD1"), "0"));
+    HY_CUDA(launch_row_pass((B == 1 && gspec_saved && bwd1) ? ROW_CONV_BWD1 : ROW_CONV_BWD, a, n, s));   // A <- rows of dg, A3 <- rows of dk
     a.src = dy_pre; a.src2 = c_saved; a.out2 = ds_scratch; a.red = dfbias; a.dsw = dsw; a.dsb = dsb;
     HY_CUDA(launch_col_inv(INV_BWD_DG, a, n * B, s));
     a.B = 1; a.out = dk;

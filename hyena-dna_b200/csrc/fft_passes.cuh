@@ -141,7 +141,7 @@ __device__ __forceinline__ float2 staged_pair(const float* st, int rr, int col) 
 // ------------------------------------------------------------------------------------------------
 enum ColMode { COL_FILTER = 0, COL_GATE = 1, COL_DC = 2, COL_PLAIN = 3 };
 enum InvMode { INV_CONV_FWD = 0, INV_BWD_DG = 1, INV_DK = 2, INV_PLAIN_FWD = 3, INV_PLAIN_BWD = 4 };
-enum RowMode { ROW_FILTER = 0, ROW_CONV_FWD = 1, ROW_CONV_BWD = 2 };
+enum RowMode { ROW_FILTER = 0, ROW_CONV_FWD = 1, ROW_CONV_BWD = 2, ROW_CONV_BWD1 = 3 };
 
 // Rows of one launch are numbered r = ci*B + b (all batches of a channel adjacent), channel c = c0 + ci.
 struct PassArgs {
@@ -725,11 +725,14 @@ __device__ __forceinline__ void even_odd(float2 z, float2 pc, float2& e, float2&
 // exchange area); CONV_BWD: rows*(EX + M2) (dc spectrum separate, g spectrum aliased onto the exchange area)
 template <int MODE, int LOGM2>
 __host__ __device__ constexpr size_t row_smem_elems(int rows) {
-  return (size_t)rows * (RowGeo<LOGM2>::EX + (MODE == ROW_CONV_BWD ? RowGeo<LOGM2>::M2 : 0));
+  return (size_t)rows * (RowGeo<LOGM2>::EX + ((MODE == ROW_CONV_BWD || MODE == ROW_CONV_BWD1) ? RowGeo<LOGM2>::M2 : 0));
 }
 
+// ROW_CONV_BWD1 is the batch-1 form of ROW_CONV_BWD with the spectrum of g saved by the forward pass: no register
+// accumulator across the batch, so it fits 128 threads x <= 170 registers and three 4-row CTAs per SM instead of one
+// 8-row CTA at 255 registers (the dc spectrum stays in shared memory between the two pointwise/inverse phases).
 template <int MODE, int LOGM2>
-__global__ void __launch_bounds__(256, MODE == ROW_CONV_BWD ? 1 : 2)
+__global__ void __launch_bounds__(MODE == ROW_CONV_BWD1 ? 128 : 256, MODE == ROW_CONV_BWD ? 1 : (MODE == ROW_CONV_BWD1 ? 3 : 2))
 row_pass_kernel(const PassArgs a) {
   using RG = RowGeo<LOGM2>;
   constexpr int M2 = RG::M2, TPR = RG::TPR;
@@ -791,6 +794,45 @@ row_pass_kernel(const PassArgs a) {
       });
       __syncthreads();                                  // partner rows are done reading this row's spectrum
       row_ifft_store<LOGM2>(v, ex, Arow, q, id.k1, logM, a.T, rsync);
+    } else if constexpr (MODE == ROW_CONV_BWD1) {
+      const int ci = blockIdx.y, c = a.c0 + ci;          // B == 1: row index == channel index of the group
+      const float2* Krow = a.kspec + (size_t)c * rowElems + (size_t)id.k1 * M2;
+      const float2* Kprow = a.kspec + (size_t)c * rowElems + (size_t)id.pk1 * M2;
+      const float2* Grow = a.gspec + (size_t)c * rowElems + (size_t)id.k1 * M2;
+      const float2* Gprow = a.gspec + (size_t)c * rowElems + (size_t)id.pk1 * M2;
+      float2* Drow = a.A + (size_t)ci * rowElems + (size_t)id.k1 * M2;
+      row_fft_to_smem<LOGM2>(Drow, ex, zbuf, q, a.T, rsync);       // dc spectrum -> zbuf (kept for both phases)
+      __syncthreads();
+      float2 v[32];
+      static_for<0, 32>([&](auto s_) {                             // phase 1: dg spectrum = corr(dc, k)
+        constexpr int s = decltype(s_)::value;
+        const int k2 = TPR * s + q;
+        const int pc = (M2 - k2 - id.nz) & (M2 - 1);
+        float2 E, O, He, Ho;
+        even_odd(zbuf[k2], cconj(zbufp[pc]), E, O);
+        even_odd(__ldg(Krow + k2), cconj(__ldg(Kprow + pc)), He, Ho);
+        const float2 WE = cmulc(E, mul_w32<s, false>(wbase));
+        float2 Ye = cadd(cmulc(E, He), cmulc(O, Ho));
+        float2 Yo = cadd(cmulc(WE, Ho), cmulc(O, He));
+        v[s] = cadd(Ye, cmul_i(Yo));
+      });
+      row_ifft_store<LOGM2>(v, ex, Drow, q, id.k1, logM, a.T, rsync);
+      rsync();
+      asm volatile("" : "+l"(Grow), "+l"(Gprow));                  // keep phase 2's loads behind phase 1 (registers)
+      static_for<0, 32>([&](auto s_) {                             // phase 2: dk spectrum = corr(dc, g)
+        constexpr int s = decltype(s_)::value;
+        const int k2 = TPR * s + q;
+        const int pc = (M2 - k2 - id.nz) & (M2 - 1);
+        float2 E, O, Ge, Go;
+        even_odd(zbuf[k2], cconj(zbufp[pc]), E, O);
+        even_odd(__ldg(Grow + k2), cconj(__ldg(Gprow + pc)), Ge, Go);
+        const float2 WE = cmulc(E, mul_w32<s, false>(wbase));
+        float2 Ke = cadd(cmulc(E, Ge), cmulc(O, Go));
+        float2 Ko = cadd(cmulc(WE, Go), cmulc(O, Ge));
+        v[s] = cadd(Ke, cmul_i(Ko));
+      });
+      float2* Krow_out = a.A3 + (size_t)ci * rowElems + (size_t)id.k1 * M2;
+      row_ifft_store<LOGM2>(v, ex, Krow_out, q, id.k1, logM, a.T, rsync);
     } else {   // ROW_CONV_BWD: loop over the batch, accumulate dK' in registers
       const int ci = blockIdx.y, c = a.c0 + ci;
       const float2* Krow = a.kspec + (size_t)c * rowElems + (size_t)id.k1 * M2;
