@@ -318,3 +318,30 @@ def test_host_step_matches_autograd(B, L, D):
     _close(duh, ug.grad, "host du")
     for g, p in zip(gh, params):
         _close(g, p.grad, "host grad", rtol=2e-3, atol=2e-5)
+
+
+# ------------------------------------------------------------------------------------------ BASELINE.json configs
+@pytest.mark.parametrize("name,B,L,D", [("small-32k", 8, 32768, 256), ("medium-160k", 4, 160000, 256)])
+def test_baseline_configs_full_size_against_fp32_oracle(name, B, L, D):
+    """BASELINE.json configs[1] and [2] at full size, fwd+bwd, against the oracle run in fp32 on the host (the
+    reference's own path) -- judged with the north_star tolerance, normwise where cancellation dominates."""
+    dev = _dev()
+    torch.set_num_threads(min(16, torch.get_num_threads()))
+    g = torch.Generator().manual_seed(42)
+    P = O.init_params(D, L, emb_dim=5, w=10.0, generator=g, init_std=0.02)
+    u, _ = O.nucleotide_activations(B, L, D, seed=2222)
+    dy = torch.randn(B, L, D, generator=torch.Generator().manual_seed(1))
+    y_ref, du_ref, g_ref = O.operator_fwd_bwd(u, P, dy)
+    sd = dict(P)
+    for extra in ("filter_fn.implicit_filter.3.freq", "filter_fn.implicit_filter.5.freq"):
+        sd[extra] = sd["filter_fn.implicit_filter.1.freq"]
+    op = _module_from_sd(sd, D, L, 5, 10.0, dev)
+    ug = u.to(dev).requires_grad_(True)
+    y = op(ug)
+    y.backward(dy.to(dev))
+    _close(y, y_ref, f"{name} y")
+    _close(ug.grad, du_ref, f"{name} du")
+    got = dict(op.named_parameters())
+    for n in ("filter_fn.bias", "short_filter.weight", "short_filter.bias", "in_proj.weight", "out_proj.weight",
+              "filter_fn.implicit_filter.6.weight", "filter_fn.implicit_filter.0.weight"):
+        _close(got[n].grad, g_ref[n], f"{name} grad {n}", rtol=3e-3, atol=3e-5)
