@@ -34,6 +34,7 @@ SIGNATURES = {
     "hyena_b200_filter_bwd": (_i, [c_fp, _i, c_fp] + [c_fp] * 7 + [c_fp, c_fp, _f, _i, _i, _i, _i, _i, c_fp]
                               + [c_fp] * 8 + [c_fp, _i, _vp]),
     "hyena_b200_filter_bwd_stage1": (_i, [c_fp, _i, c_fp] + [c_fp] * 7 + [c_fp, c_fp, _f, _i, _i, _i, _i, _i, c_fp, c_fp, c_fp, _vp]),
+    "hyena_b200_filter_bwd_stage2": (_i, [c_fp] * 11 + [_i, _i, _i, _vp]),
     "hyena_b200_filter_spectrum": (_i, [c_fp, c_fp, _i, _i, _vp, _sz, _vp]),
     "hyena_b200_core_fwd": (_i, [c_fp] * 9 + [_i, _i, _i, _vp, _sz, _vp]),
     "hyena_b200_core_bwd": (_i, [c_fp] * 16 + [_i, _i, _i, _vp, _sz, _vp]),
@@ -96,7 +97,7 @@ def profile_begin():
 
 def profile_end():
     """-> {kernel class: (device ms, launches)} for the window opened by profile_begin()."""
-    n = 19
+    n = 20
     ms = (ctypes.c_double * n)()
     cnt = (ctypes.c_ulonglong * n)()
     check(lib().hyena_b200_profile_end(ms, cnt, n))

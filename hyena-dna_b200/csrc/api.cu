@@ -214,7 +214,7 @@ HY_API const char* hyena_b200_kind_name(int kind) {
       "col_fwd<filter>", "col_fwd<gate>", "col_fwd<dc>", "col_fwd<plain>",
       "col_inv<conv_fwd>", "col_inv<bwd_dg>", "col_inv<dk>", "col_inv<plain_fwd>", "col_inv<plain_bwd>",
       "row_pass<filter>", "row_pass<conv_fwd>", "row_pass<conv_bwd>",
-      "filter_fwd", "filter_bwd", "short_conv_bwd", "twiddle_init", "filter_tc_prep", "filter_tc_fwd", "filter_tc_bwd"};
+      "filter_fwd", "filter_bwd", "short_conv_bwd", "twiddle_init", "filter_tc_prep", "filter_tc_fwd", "filter_tc_bwd", "filter_tc_red"};
   return (kind >= 0 && kind < K_COUNT) ? names[kind] : "?";
 }
 
@@ -310,6 +310,18 @@ HY_API int hyena_b200_filter_bwd_stage1(const float* z, int z_stride, const floa
   float* wimg = nullptr;
   if (get_wimg(D, (cudaStream_t)stream, &wimg)) return 1;
   HY_CUDA(launch_filter_bwd_tc(P, wimg, dk, dh, scratch, (cudaStream_t)stream));
+  return 0;
+}
+
+HY_API int hyena_b200_filter_bwd_stage2(const float* dh, const float* scratch, const float* zT, float* dW0, float* db0,
+                                 float* dW1, float* db1, float* dW2, float* db2, float* dW3, float* dfreq, int L,
+                                 int E, int D, void* stream) {
+  HY_CHECK(dh && scratch && zT && dW0 && db0 && dW1 && db1 && dW2 && db2 && dW3 && dfreq, "null pointer");
+  HY_CHECK(D >= 1 && D <= 256 && E >= 1 && E <= 8 && L >= 1, "fused filter reduction handles D <= 256, E <= 8 (got D=%d E=%d)", D, E);
+  HY_CHECK((reinterpret_cast<uintptr_t>(dh) & 15u) == 0 && (reinterpret_cast<uintptr_t>(scratch) & 15u) == 0 &&
+               (reinterpret_cast<uintptr_t>(zT) & 15u) == 0, "misaligned pointer");
+  RedLaunch r{dh, scratch, zT, dW0, db0, dW1, db1, dW2, db2, dW3, dfreq, L, D, E};
+  HY_CUDA(launch_filter_red_tc(r, (cudaStream_t)stream));
   return 0;
 }
 

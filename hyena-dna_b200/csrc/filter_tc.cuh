@@ -339,7 +339,7 @@ filter_tc_fwd_kernel(const FilterParams P, const float* __restrict__ wimg, float
 // Per 128-position tile, all GEMMs with M = positions (thread = position, same operand builders as forward):
 //   recompute pre1..3 / a1..3;  da3 = dh W3 (dh = dk * modulation, K = channels in chunks of 64);
 //   dp3 = da3 f cos(f pre3);  da2 = dp3 W2;  dp2 = ...;  da1 = dp2 W1;  dp1 = ...
-// and writes, position-major [t][64]: a1, a2, a3, dp1, dp2, dp3, X = sum_l da_l cos(f pre_l) pre_l, plus dh (D, L).
+// and writes, feature-major (64, L): a1, a2, a3, dp1, dp2, dp3, X = sum_l da_l cos(f pre_l) pre_l, plus dh (D, L).
 // Stage 2 (host side, hyena-dna_b200/ops.py) turns those into the parameter gradients with GEMMs whose reduction
 // dimension is the sequence: dW3 = dh a3, dW2 = dp3^T a2, dW1 = dp2^T a1, dW0 = dp1^T z, db_l = colsum(dp_l),
 // dfreq = colsum(X), dz = dp1 W0.
@@ -381,9 +381,11 @@ __device__ __forceinline__ void stream_item(unsigned char* smem, const float* wi
   for (int i = tid; i < 2 * kImgW64 / 4; i += kThreads) cp_async16(dst + 16 * i, src + 4 * i, true);
 }
 
-__device__ __forceinline__ void store16(float* dst, const float (&a)[16]) {
+// 16 features of one position into a feature-major (64, L) array: for a fixed feature the 32 lanes of a warp write
+// 32 consecutive positions (128 bytes)
+__device__ __forceinline__ void store16(float* dst, size_t L, const float (&a)[16]) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+  for (int i = 0; i < 16; ++i) dst[(size_t)i * L] = a[i];
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -434,7 +436,7 @@ filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int t = tile * kTileM + row;
     const bool tv = t < P.L;
-    float* out = scratch + (size_t)(tv ? t : 0) * 64 + part * 16;
+    float* out = scratch + (size_t)(part * 16) * P.L + (tv ? t : 0);      // [array][feature][t]
     stream_item(smem, wimg, 0, tid);
     stream_item(smem, wimg, 1, tid);
 
@@ -454,7 +456,7 @@ filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const
         a[j] = sin_ni(fr[j] * acc);
       }
       store_row_split<16>(smem, row, part * 16, a);
-      if (tv) store16(out + 0 * arr, a);
+      if (tv) store16(out + 0 * arr, P.L, a);
     }
     fence_async_smem();
     __syncthreads();
@@ -468,7 +470,7 @@ filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const
 #pragma unroll
     for (int j = 0; j < 16; ++j) { pre2[j] += b1s[part * 16 + j]; a[j] = sin_ni(fr[j] * pre2[j]); }
     store_row_split<16>(smem, row, part * 16, a);
-    if (tv) store16(out + 1 * arr, a);
+    if (tv) store16(out + 1 * arr, P.L, a);
     fence_before_sync();
     fence_async_smem();
     __syncthreads();
@@ -481,7 +483,7 @@ filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const
     tmem_ld16(lane_addr + part * 16, pre3);
 #pragma unroll
     for (int j = 0; j < 16; ++j) { pre3[j] += b2s[part * 16 + j]; a[j] = sin_ni(fr[j] * pre3[j]); }
-    if (tv) store16(out + 2 * arr, a);
+    if (tv) store16(out + 2 * arr, P.L, a);
     fence_before_sync();
 
     // ---- da3 = dh W3, 64 channels per MMA group; dh = dk * (exp(-t|delta|) + shift) also goes to HBM (stage 2 needs it)
@@ -546,7 +548,7 @@ filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const
       X[j] = g * pre3[j];
       a[j] = g * fr[j];
     }
-    if (tv) store16(out + 5 * arr, a);
+    if (tv) store16(out + 5 * arr, P.L, a);
     store_row_split<16>(smem, row, part * 16, a);
     cp_async_wait_all();
     fence_before_sync();
@@ -567,7 +569,7 @@ filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const
       X[j] = fmaf(g, pre2[j], X[j]);
       a[j] = g * fr[j];
     }
-    if (tv) store16(out + 4 * arr, a);
+    if (tv) store16(out + 4 * arr, P.L, a);
     store_row_split<16>(smem, row, part * 16, a);
     fence_before_sync();
     fence_async_smem();
@@ -587,7 +589,7 @@ filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const
       X[j] = fmaf(g, pre1[j], X[j]);
       a[j] = g * fr[j];
     }
-    if (tv) { store16(out + 3 * arr, a); store16(out + 6 * arr, X); }
+    if (tv) { store16(out + 3 * arr, P.L, a); store16(out + 6 * arr, P.L, X); }
     fence_before_sync();
     __syncthreads();
   }
@@ -595,6 +597,227 @@ filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const
   __syncthreads();
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- backward, stage 2
+// All parameter gradients of the filter are reductions over the sequence.  With the stage-1 arrays stored feature-
+// major every operand is K-major with K = position, so they are three accumulating tcgen05 GEMM groups whose fp32
+// accumulators stay in tensor memory for the whole kernel (persistent CTAs, split over the sequence, one atomic
+// flush at the end):
+//   G1  dW3[c][j]      = sum_t dh[c][t] a3[j][t]                       M = 128 channels per tile (<= 2 tiles), N = 64
+//   G2  [dp3;dp2] x [a2;a1;1]^T : block(0,0) = dW2, block(1,1) = dW1, column 128 = (db2 ; db1)     M = 128, N = 144
+//   G3  [dp1;X]  x [z;1]^T      : rows 0..63 -> (dW0 | db0), rows 64..127 col 8 -> dfreq             M = 128, N = 16
+// K block = 32 positions (operand images: K-major, SBO 1024 B, LBO 128 B), 3xTF32 like everywhere else.
+constexpr int kRedKB = 32;
+constexpr uint32_t kRedSBO = 1024;
+__host__ __device__ constexpr uint32_t red_off(int r, int k) {
+  return (uint32_t)((r >> 3) * 1024 + (k >> 2) * 128 + (r & 7) * 16 + (k & 3) * 4);
+}
+constexpr uint32_t kRedImg128 = 128 * kRedKB * 4;      // bytes of a 128-row image (16 KB)
+// shared memory map (bytes); every operand has a hi image followed by a lo image
+constexpr uint32_t kRedOffDh = 0;                                  // 2 tiles x (hi 16K + lo 16K) = 64 KB
+constexpr uint32_t kRedOffAs = 65536;                              // [dp3;dp2]   32 KB
+constexpr uint32_t kRedOffAx = kRedOffAs + 32768;                  // [dp1;X]     32 KB
+constexpr uint32_t kRedOffB3 = kRedOffAx + 32768;                  // a3 (64 rows): hi 8K + lo 8K
+constexpr uint32_t kRedOffBs = kRedOffB3 + 16384;                  // [a2;a1;ones16] 144 rows: hi 18K + lo 18K
+constexpr uint32_t kRedOffBz = kRedOffBs + 36864;                  // [z pad 8; ones 8] 16 rows: hi 2K + lo 2K
+constexpr uint32_t kRedOffMisc = kRedOffBz + 4096;
+constexpr size_t kRedSmemBytes = kRedOffMisc + 64;
+constexpr int kRedTmemCols = 512;                                  // G1: [0,128)  G2: [128,272)  G3: [272,288)
+
+__device__ __forceinline__ uint64_t make_desc_red(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(kLBO >> 4) << 16;
+  d |= (uint64_t)(kRedSBO >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__device__ __forceinline__ void issue_red(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                          int N, uint32_t first_acc) {
+  const uint32_t idesc = make_idesc(N);
+  uint32_t acc = first_acc;
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {
+    const uint32_t a = (pass == 1) ? a_lo : a_hi;
+    const uint32_t b = (pass == 2) ? b_lo : b_hi;
+#pragma unroll
+    for (int ks = 0; ks < kRedKB / 8; ++ks) {
+      mma_tf32(tmem_d, make_desc_red(a + ks * 2 * kLBO), make_desc_red(b + ks * 2 * kLBO), idesc, acc);
+      acc = 1;
+    }
+  }
+}
+
+// four consecutive positions of a feature row (zero beyond L); vector load when rows are 16-byte aligned
+__device__ __forceinline__ float4 load4_row(const float* __restrict__ src, size_t t, size_t L, bool v4) {
+  float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (v4 && t + 3 < L) return __ldg(reinterpret_cast<const float4*>(src + t));
+  if (t < L) x.x = __ldg(src + t);
+  if (t + 1 < L) x.y = __ldg(src + t + 1);
+  if (t + 2 < L) x.z = __ldg(src + t + 2);
+  if (t + 3 < L) x.w = __ldg(src + t + 3);
+  return x;
+}
+
+struct RedArgs {
+  const float* dh;        // (D, L)
+  const float* scratch;   // (7, 64, L): a1 a2 a3 dp1 dp2 dp3 X
+  const float* zT;        // (E, L)
+  float* dW0; float* db0; float* dW1; float* db1; float* dW2; float* db2; float* dW3; float* dfreq;
+  int L, D, E;
+};
+
+__global__ void __launch_bounds__(256, 1) filter_tc_red_kernel(const RedArgs R, int nblocks) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* mbar_p = reinterpret_cast<uint64_t*>(smem + kRedOffMisc);
+  uint32_t* tmem_p = reinterpret_cast<uint32_t*>(mbar_p + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t mbar = smem_u32(mbar_p);
+  const int nmt = (R.D + 127) / 128;                       // channel tiles (host guarantees <= 2)
+  const size_t L = (size_t)R.L;
+  const bool v4 = (R.L & 3) == 0;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_p)), "r"(kRedTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) mbar_init(mbar, 1);
+  // zero every image once (rows that are never loaded -- channel padding, z padding -- stay zero), then the ones rows
+  for (uint32_t i = tid; i < kRedOffMisc / 16; i += 256) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  for (int i = tid; i < 16 * kRedKB; i += 256) {           // [a2;a1;ones16]: rows 128..143 hi = 1
+    const int r = 128 + i / kRedKB, k = i % kRedKB;
+    *reinterpret_cast<float*>(smem + kRedOffBs + red_off(r, k)) = 1.f;
+  }
+  for (int i = tid; i < 8 * kRedKB; i += 256) {            // [z;ones8]: rows 8..15 hi = 1
+    const int r = 8 + i / kRedKB, k = i % kRedKB;
+    *reinterpret_cast<float*>(smem + kRedOffBz + red_off(r, k)) = 1.f;
+  }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tmem_p;
+
+  // rows to load per k-block: (dst image base, hi->lo distance, dst row, source row pointer)
+  // piece p of a row = 4 consecutive positions; 8 pieces per row.  Work items are (row, piece) pairs.
+  const int rows_dh = R.D;                                 // rows [0, D) of dh
+  const int nrow = rows_dh + 6 * 64 + R.E;
+  uint32_t phase = 0;
+  bool first = true;
+  for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const size_t t0 = (size_t)blk * kRedKB;
+    if (!first) { mbar_wait(mbar, phase); phase ^= 1; fence_after_sync(); }   // previous MMAs have read the images
+    for (int w = tid; w < nrow * 8; w += 256) {
+      const int row = w >> 3, pc = w & 7;
+      const float* src;
+      uint32_t img, lo_off;
+      int r;
+      if (row < rows_dh) {                                 // dh channel row -> tile row/128
+        src = R.dh + (size_t)row * L;
+        img = kRedOffDh + (row >> 7) * 32768; lo_off = 16384; r = row & 127;
+      } else {
+        const int q = row - rows_dh;
+        if (q < 6 * 64) {
+          const int arr = q >> 6, f = q & 63;              // scratch order: a1 a2 a3 dp1 dp2 dp3 (X handled below)
+          src = R.scratch + ((size_t)arr * 64 + f) * L;
+          switch (arr) {
+            case 0: img = kRedOffBs; lo_off = 18432; r = 64 + f; break;      // a1 -> B_s rows 64..127
+            case 1: img = kRedOffBs; lo_off = 18432; r = f; break;           // a2 -> B_s rows 0..63
+            case 2: img = kRedOffB3; lo_off = 8192; r = f; break;            // a3
+            case 3: img = kRedOffAx; lo_off = 16384; r = f; break;           // dp1 -> A_x rows 0..63
+            case 4: img = kRedOffAs; lo_off = 16384; r = 64 + f; break;      // dp2 -> A_s rows 64..127
+            default: img = kRedOffAs; lo_off = 16384; r = f; break;          // dp3 -> A_s rows 0..63
+          }
+        } else {
+          const int e = q - 6 * 64;                        // z feature e -> B_z row e
+          src = R.zT + (size_t)e * L;
+          img = kRedOffBz; lo_off = 2048; r = e;
+        }
+      }
+      const float4 x = load4_row(src, t0 + 4 * pc, L, v4);
+      float4 hi, lo;
+      split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y); split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
+      const uint32_t off = img + red_off(r, 4 * pc);
+      *reinterpret_cast<float4*>(smem + off) = hi;
+      *reinterpret_cast<float4*>(smem + off + lo_off) = lo;
+    }
+    // X (scratch array 6) -> A_x rows 64..127
+    for (int w = tid; w < 64 * 8; w += 256) {
+      const int f = w >> 3, pc = w & 7;
+      const float* src = R.scratch + ((size_t)6 * 64 + f) * L;
+      const float4 x = load4_row(src, t0 + 4 * pc, L, v4);
+      float4 hi, lo;
+      split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y); split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
+      const uint32_t off = kRedOffAx + red_off(64 + f, 4 * pc);
+      *reinterpret_cast<float4*>(smem + off) = hi;
+      *reinterpret_cast<float4*>(smem + off + 16384) = lo;
+    }
+    fence_before_sync();
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      const uint32_t acc0 = first ? 0u : 1u;
+      for (int mt = 0; mt < nmt; ++mt)
+        issue_red(tmem + mt * 64, sbase + kRedOffDh + mt * 32768, sbase + kRedOffDh + mt * 32768 + 16384,
+                  sbase + kRedOffB3, sbase + kRedOffB3 + 8192, 64, acc0);
+      issue_red(tmem + 128, sbase + kRedOffAs, sbase + kRedOffAs + 16384, sbase + kRedOffBs, sbase + kRedOffBs + 18432, 144, acc0);
+      issue_red(tmem + 272, sbase + kRedOffAx, sbase + kRedOffAx + 16384, sbase + kRedOffBz, sbase + kRedOffBz + 2048, 16, acc0);
+      mma_commit(mbar);
+    }
+    first = false;
+  }
+  if (!first) { mbar_wait(mbar, phase); phase ^= 1; fence_after_sync(); }
+
+  // ---- flush: warps 0..3 own TMEM lanes 32*(w%4)..; warps 4..7 take the second half of the columns
+  if (!first) {
+    const int row = 32 * (warp & 3) + lane;                // accumulator row (TMEM lane)
+    const int half = warp >> 2;
+    const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+    float v[32];
+    for (int mt = 0; mt < nmt; ++mt) {                     // G1: dW3 rows c = 128 mt + row, 64 columns (32 per half)
+      tmem_ld32(lane_addr + mt * 64 + half * 32, v);
+      const int c = mt * 128 + row;
+      if (c < R.D)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(R.dW3 + (size_t)c * 64 + half * 32 + j, v[j]);
+    }
+    // G2: rows < 64: cols 0..63 -> dW2[row][j]; rows >= 64: cols 64..127 -> dW1[row-64][j]; col 128 -> db2 / db1
+    {
+      const int cbase = (row < 64) ? 0 : 64;
+      tmem_ld32(lane_addr + 128 + cbase + half * 32, v);
+      float* dst = (row < 64) ? (R.dW2 + row * 64) : (R.dW1 + (row - 64) * 64);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) atomicAdd(dst + half * 32 + j, v[j]);
+      if (half == 0) {
+        float b16[16];
+        tmem_ld16(lane_addr + 128 + 128, b16);
+        atomicAdd(((row < 64) ? R.db2 : R.db1) + (row & 63), b16[0]);
+      }
+    }
+    // G3: rows < 64: cols 0..E-1 -> dW0[row][e], col 8 -> db0[row]; rows >= 64: col 8 -> dfreq[row-64]
+    if (half == 1) {
+      float x16[16];
+      tmem_ld16(lane_addr + 272, x16);
+      if (row < 64) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (e < R.E) atomicAdd(R.dW0 + row * R.E + e, x16[e]);
+        atomicAdd(R.db0 + row, x16[8]);
+      } else {
+        atomicAdd(R.dfreq + (row - 64), x16[8]);
+      }
+    }
+    fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kRedTmemCols) : "memory");
   }
 }
 

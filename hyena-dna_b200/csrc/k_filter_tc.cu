@@ -46,4 +46,19 @@ cudaError_t launch_filter_fwd_tc(const FilterParams& P, float* wimg, float* kout
   return cudaGetLastError();
 }
 
+cudaError_t launch_filter_red_tc(const RedLaunch& r, cudaStream_t s) {
+  cudaError_t e = set_smem(tc::filter_tc_red_kernel, tc::kRedSmemBytes);
+  if (e != cudaSuccess) return e;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  tc::RedArgs R{r.dh, r.scratch, r.zT, r.dW0, r.db0, r.dW1, r.db1, r.dW2, r.db2, r.dW3, r.dfreq, r.L, r.D, r.E};
+  const int nblocks = (r.L + tc::kRedKB - 1) / tc::kRedKB;
+  const int grid = nblocks < sms ? nblocks : sms;
+  prof_begin(K_FILTER_TC_RED, s);
+  tc::filter_tc_red_kernel<<<grid, 256, tc::kRedSmemBytes, s>>>(R, nblocks);
+  prof_end(K_FILTER_TC_RED, s);
+  return cudaGetLastError();
+}
+
 }  // namespace hy

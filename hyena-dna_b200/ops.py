@@ -81,38 +81,24 @@ def _filter_backward_tc(z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, shift, m
     dk = dk.contiguous()
     dev = z.device
     dh = torch.empty(D, L, dtype=torch.float32, device=dev)
-    sc = torch.empty(7, L, 64, dtype=torch.float32, device=dev)
+    sc = torch.empty(7, 64, L, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().hyena_b200_filter_bwd_stage1(
             _ptr(zz), zz.stride(0), _ptr(tt), *[_ptr(w) for w in ws], _ptr(fr), _ptr(dl),
             float(shift), int(bool(modulate)), int(L), E, N, D, _ptr(dk), _ptr(dh), _ptr(sc), _stream()))
-    a1, a2, a3, dp1, dp2, dp3, X = sc.unbind(0)
-    if gemm_mode() == "bf16x9":
-        dW3 = torch.empty(D, 64, dtype=torch.float32, device=dev)
-        dW2 = torch.empty(64, 64, dtype=torch.float32, device=dev)
-        dW1 = torch.empty(64, 64, dtype=torch.float32, device=dev)
-        # dW3^T (64 x D, ld 64) = a3^T (64 x L, stored, op N) dh^T (L x D, stored ld L, op N)
-        gemm(0, 0, 64, D, L, a3, 64, 0, dh, L, 0, dW3, 64, 0)
-        # dW2^T (64 j x 64 i, ld 64) = a2^T (64 x L, stored, op N) dp3 (L x 64; stored as (64 x L) -> op T)
-        gemm(0, 1, 64, 64, L, a2, 64, 0, dp3, 64, 0, dW2, 64, 0)
-        gemm(0, 1, 64, 64, L, a1, 64, 0, dp2, 64, 0, dW1, 64, 0)
-    else:
-        dW3 = dh @ a3
-        dW2 = dp3.t() @ a2
-        dW1 = dp2.t() @ a1
-    sums = sc[3:7].sum(dim=1)                       # one pass: colsum(dp1), colsum(dp2), colsum(dp3), colsum(X)
-    if gemm_mode() == "bf16x9":
-        zp = torch.zeros(L, 8, dtype=torch.float32, device=dev)
-        zp[:, :E] = zz
-        dW0p = torch.empty(64, 8, dtype=torch.float32, device=dev)
-        # dW0p^T (8 x 64, ld 8) = zp^T (8 x L, stored, op N) dp1 (L x 64; stored as (64 x L) -> op T)
-        gemm(0, 1, 8, 64, L, zp, 8, 0, dp1, 64, 0, dW0p, 8, 0)
-        dW0 = dW0p[:, :E].contiguous()
-    else:
-        dW0 = dp1.t() @ zz
-    grads = [dW0, sums[0], dW1, sums[1], dW2, sums[2], dW3]
-    dfreq = sums[3]
-    dz = (dp1 @ ws[0]) if need_dz else None
+    a1, a2, a3, dp1, dp2, dp3, X = sc.unbind(0)          # feature-major (64, L) each
+    if D <= 256 and E <= 8:
+        grads = [torch.zeros_like(w) for w in ws]
+        dfreq = torch.zeros(64, dtype=torch.float32, device=dev)
+        zT = zz.t().contiguous()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().hyena_b200_filter_bwd_stage2(
+                _ptr(dh), _ptr(sc), _ptr(zT), *[_ptr(g) for g in grads], _ptr(dfreq), int(L), E, D, _stream()))
+    else:                                             # wide models: library GEMMs with K = L
+        sums = sc[3:7].sum(dim=2)
+        grads = [dp1 @ zz, sums[0], dp2 @ a1.t(), sums[1], dp3 @ a2.t(), sums[2], dh @ a3.t()]
+        dfreq = sums[3]
+    dz = (dp1.t() @ ws[0]) if need_dz else None
     return grads, dfreq, dz
 
 

@@ -83,16 +83,21 @@ HY_API int hyena_b200_filter_bwd(const float* z, int z_stride, const float* t,
                           float* dW0, float* db0, float* dW1, float* db1, float* dW2, float* db2,
                           float* dW3, float* dfreq, float* dz, int dz_stride, void* stream);
 
-/* Tensor-core (tcgen05, 3xTF32) stage 1 of the same backward: per position it recomputes the activations and
- * back-propagates through the MLP, writing dh = dk * modulation (D,L) and seven position-major (L,64) arrays into
- * `scratch` (7*L*64 floats, 16-byte aligned): a1, a2, a3, dp1, dp2, dp3, X.  The parameter gradients are then
- * sequence-length reductions (GEMMs / column sums) the caller issues:
- *   dW3 = dh a3, dW2 = dp3^T a2, dW1 = dp2^T a1, dW0 = dp1^T z, db_l = colsum(dp_{l+1}), dfreq = colsum(X), dz = dp1 W0 */
+/* Tensor-core (tcgen05, 3xTF32) backward in two stages.  Stage 1: per position, recompute the activations and back-
+ * propagate through the MLP, writing dh = dk * modulation (D,L) and seven feature-major (64,L) arrays into `scratch`
+ * (7*64*L floats, 16-byte aligned): a1, a2, a3, dp1, dp2, dp3, X.  Stage 2: the parameter gradients are reductions
+ * over the sequence, done as accumulating tcgen05 GEMMs with K = position (all outputs (+=); zT is z transposed,
+ * (E,L)); D <= 256, E <= 8:
+ *   dW3 = dh a3^T, dW2 = dp3 a2^T, dW1 = dp2 a1^T, dW0 = dp1 z, db_l = rowsum(dp_{l+1}), dfreq = rowsum(X) */
 HY_API int hyena_b200_filter_bwd_stage1(const float* z, int z_stride, const float* t,
                                  const float* W0, const float* b0, const float* W1, const float* b1,
                                  const float* W2, const float* b2, const float* W3,
                                  const float* freq, const float* deltas, float shift, int modulate,
                                  int L, int E, int N, int D, const float* dk, float* dh, float* scratch, void* stream);
+
+HY_API int hyena_b200_filter_bwd_stage2(const float* dh, const float* scratch, const float* zT,
+                                 float* dW0, float* db0, float* dW1, float* db1, float* dW2, float* db2,
+                                 float* dW3, float* dfreq, int L, int E, int D, void* stream);
 
 /* ---- filter spectrum -------------------------------------------------------------------------
  * replaces `k_f = torch.fft.rfft(k, n=fft_size) / fft_size` (hyena.py:62, src/ops/fftconv.py:65). */
