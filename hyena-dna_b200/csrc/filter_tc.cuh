@@ -610,6 +610,8 @@ filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const
 //   G3  [dp1;X]  x [z;1]^T      : rows 0..63 -> (dW0 | db0), rows 64..127 col 8 -> dfreq             M = 128, N = 16
 // K block = 32 positions (operand images: K-major, SBO 1024 B, LBO 128 B), 3xTF32 like everywhere else.
 constexpr int kRedKB = 32;
+constexpr int kRedThreads = 512;
+constexpr int kRedItems = 12;                // ceil((256 + 7*64 + 8) * 8 / 512)
 constexpr uint32_t kRedSBO = 1024;
 __host__ __device__ constexpr uint32_t red_off(int r, int k) {
   return (uint32_t)((r >> 3) * 1024 + (k >> 2) * 128 + (r & 7) * 16 + (k & 3) * 4);
@@ -669,7 +671,7 @@ struct RedArgs {
   int L, D, E;
 };
 
-__global__ void __launch_bounds__(256, 1) filter_tc_red_kernel(const RedArgs R, int nblocks) {
+__global__ void __launch_bounds__(kRedThreads, 1) filter_tc_red_kernel(const RedArgs R, int nblocks) {
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* mbar_p = reinterpret_cast<uint64_t*>(smem + kRedOffMisc);
   uint32_t* tmem_p = reinterpret_cast<uint32_t*>(mbar_p + 1);
@@ -687,13 +689,13 @@ __global__ void __launch_bounds__(256, 1) filter_tc_red_kernel(const RedArgs R, 
   }
   if (tid == 0) mbar_init(mbar, 1);
   // zero every image once (rows that are never loaded -- channel padding, z padding -- stay zero), then the ones rows
-  for (uint32_t i = tid; i < kRedOffMisc / 16; i += 256) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (uint32_t i = tid; i < kRedOffMisc / 16; i += kRedThreads) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
-  for (int i = tid; i < 16 * kRedKB; i += 256) {           // [a2;a1;ones16]: rows 128..143 hi = 1
+  for (int i = tid; i < 16 * kRedKB; i += kRedThreads) {   // [a2;a1;ones16]: rows 128..143 hi = 1
     const int r = 128 + i / kRedKB, k = i % kRedKB;
     *reinterpret_cast<float*>(smem + kRedOffBs + red_off(r, k)) = 1.f;
   }
-  for (int i = tid; i < 8 * kRedKB; i += 256) {            // [z;ones8]: rows 8..15 hi = 1
+  for (int i = tid; i < 8 * kRedKB; i += kRedThreads) {    // [z;ones8]: rows 8..15 hi = 1
     const int r = 8 + i / kRedKB, k = i % kRedKB;
     *reinterpret_cast<float*>(smem + kRedOffBz + red_off(r, k)) = 1.f;
   }
@@ -703,60 +705,66 @@ __global__ void __launch_bounds__(256, 1) filter_tc_red_kernel(const RedArgs R, 
   fence_after_sync();
   const uint32_t tmem = *tmem_p;
 
-  // rows to load per k-block: (dst image base, hi->lo distance, dst row, source row pointer)
-  // piece p of a row = 4 consecutive positions; 8 pieces per row.  Work items are (row, piece) pairs.
-  const int rows_dh = R.D;                                 // rows [0, D) of dh
-  const int nrow = rows_dh + 6 * 64 + R.E;
+  // Work items: (row, 4-position piece) pairs, 8 pieces per row; item w = tid + kRedThreads*it, so every item of a
+  // thread has the same piece index tid & 7.  The decode (source row pointer, destination offset, hi->lo distance
+  // class) does not depend on the k-block: done once, kept in registers, so that all loads of a block can be issued
+  // back to back (one DRAM latency per block instead of one per item).
+  const int nrow = R.D + 7 * 64 + R.E;                     // dh rows, six (64,L) arrays + X, z rows
+  const int pc = tid & 7;
+  const float* sp[kRedItems];
+  uint32_t dof[kRedItems];                                 // bits [0,18): byte offset of the hi piece; [18,20): lo class
+  static_for<0, kRedItems>([&](auto it_) {
+    constexpr int it = decltype(it_)::value;
+    const int row = (tid + kRedThreads * it) >> 3;
+    const float* src = nullptr;
+    uint32_t img = 0, cls = 0;
+    int r = 0;
+    if (row < R.D) {
+      src = R.dh + (size_t)row * L; img = kRedOffDh + (row >> 7) * 32768; cls = 0; r = row & 127;
+    } else if (row < nrow) {
+      const int q = row - R.D;
+      if (q < 7 * 64) {
+        const int arr = q >> 6, f = q & 63;                // scratch order: a1 a2 a3 dp1 dp2 dp3 X
+        src = R.scratch + ((size_t)arr * 64 + f) * L;
+        switch (arr) {
+          case 0: img = kRedOffBs; cls = 1; r = 64 + f; break;      // a1  -> B_s rows 64..127
+          case 1: img = kRedOffBs; cls = 1; r = f; break;           // a2  -> B_s rows 0..63
+          case 2: img = kRedOffB3; cls = 2; r = f; break;           // a3
+          case 3: img = kRedOffAx; cls = 0; r = f; break;           // dp1 -> A_x rows 0..63
+          case 4: img = kRedOffAs; cls = 0; r = 64 + f; break;      // dp2 -> A_s rows 64..127
+          case 5: img = kRedOffAs; cls = 0; r = f; break;           // dp3 -> A_s rows 0..63
+          default: img = kRedOffAx; cls = 0; r = 64 + f; break;     // X   -> A_x rows 64..127
+        }
+      } else {
+        const int e = q - 7 * 64;                          // z feature e -> B_z row e
+        src = R.zT + (size_t)e * L; img = kRedOffBz; cls = 3; r = e;
+      }
+    }
+    sp[it] = src;
+    dof[it] = (img + red_off(r, 4 * pc)) | (cls << 18);
+  });
   uint32_t phase = 0;
   bool first = true;
   for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
-    const size_t t0 = (size_t)blk * kRedKB;
+    const size_t t = (size_t)blk * kRedKB + 4 * pc;
+    float4 x[kRedItems];
+    static_for<0, kRedItems>([&](auto it_) {               // all loads of this block in flight at once
+      constexpr int it = decltype(it_)::value;
+      x[it] = sp[it] ? load4_row(sp[it], t, L, v4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    });
     if (!first) { mbar_wait(mbar, phase); phase ^= 1; fence_after_sync(); }   // previous MMAs have read the images
-    for (int w = tid; w < nrow * 8; w += 256) {
-      const int row = w >> 3, pc = w & 7;
-      const float* src;
-      uint32_t img, lo_off;
-      int r;
-      if (row < rows_dh) {                                 // dh channel row -> tile row/128
-        src = R.dh + (size_t)row * L;
-        img = kRedOffDh + (row >> 7) * 32768; lo_off = 16384; r = row & 127;
-      } else {
-        const int q = row - rows_dh;
-        if (q < 6 * 64) {
-          const int arr = q >> 6, f = q & 63;              // scratch order: a1 a2 a3 dp1 dp2 dp3 (X handled below)
-          src = R.scratch + ((size_t)arr * 64 + f) * L;
-          switch (arr) {
-            case 0: img = kRedOffBs; lo_off = 18432; r = 64 + f; break;      // a1 -> B_s rows 64..127
-            case 1: img = kRedOffBs; lo_off = 18432; r = f; break;           // a2 -> B_s rows 0..63
-            case 2: img = kRedOffB3; lo_off = 8192; r = f; break;            // a3
-            case 3: img = kRedOffAx; lo_off = 16384; r = f; break;           // dp1 -> A_x rows 0..63
-            case 4: img = kRedOffAs; lo_off = 16384; r = 64 + f; break;      // dp2 -> A_s rows 64..127
-            default: img = kRedOffAs; lo_off = 16384; r = f; break;          // dp3 -> A_s rows 0..63
-          }
-        } else {
-          const int e = q - 6 * 64;                        // z feature e -> B_z row e
-          src = R.zT + (size_t)e * L;
-          img = kRedOffBz; lo_off = 2048; r = e;
-        }
+    static_for<0, kRedItems>([&](auto it_) {
+      constexpr int it = decltype(it_)::value;
+      if (sp[it]) {
+        float4 hi, lo;
+        split_tf32(x[it].x, hi.x, lo.x); split_tf32(x[it].y, hi.y, lo.y);
+        split_tf32(x[it].z, hi.z, lo.z); split_tf32(x[it].w, hi.w, lo.w);
+        const uint32_t off = dof[it] & 0x3FFFFu, cls = dof[it] >> 18;
+        const uint32_t lo_off = cls == 0 ? 16384u : cls == 1 ? 18432u : cls == 2 ? 8192u : 2048u;
+        *reinterpret_cast<float4*>(smem + off) = hi;
+        *reinterpret_cast<float4*>(smem + off + lo_off) = lo;
       }
-      const float4 x = load4_row(src, t0 + 4 * pc, L, v4);
-      float4 hi, lo;
-      split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y); split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
-      const uint32_t off = img + red_off(r, 4 * pc);
-      *reinterpret_cast<float4*>(smem + off) = hi;
-      *reinterpret_cast<float4*>(smem + off + lo_off) = lo;
-    }
-    // X (scratch array 6) -> A_x rows 64..127
-    for (int w = tid; w < 64 * 8; w += 256) {
-      const int f = w >> 3, pc = w & 7;
-      const float* src = R.scratch + ((size_t)6 * 64 + f) * L;
-      const float4 x = load4_row(src, t0 + 4 * pc, L, v4);
-      float4 hi, lo;
-      split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y); split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
-      const uint32_t off = kRedOffAx + red_off(64 + f, 4 * pc);
-      *reinterpret_cast<float4*>(smem + off) = hi;
-      *reinterpret_cast<float4*>(smem + off + 16384) = lo;
-    }
+    });
     fence_before_sync();
     fence_async_smem();
     __syncthreads();
@@ -775,7 +783,7 @@ __global__ void __launch_bounds__(256, 1) filter_tc_red_kernel(const RedArgs R, 
   if (!first) { mbar_wait(mbar, phase); phase ^= 1; fence_after_sync(); }
 
   // ---- flush: warps 0..3 own TMEM lanes 32*(w%4)..; warps 4..7 take the second half of the columns
-  if (!first) {
+  if (!first && warp < 8) {
     const int row = 32 * (warp & 3) + lane;                // accumulator row (TMEM lane)
     const int half = warp >> 2;
     const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);

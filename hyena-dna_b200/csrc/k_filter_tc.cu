@@ -56,7 +56,7 @@ cudaError_t launch_filter_red_tc(const RedLaunch& r, cudaStream_t s) {
   const int nblocks = (r.L + tc::kRedKB - 1) / tc::kRedKB;
   const int grid = nblocks < sms ? nblocks : sms;
   prof_begin(K_FILTER_TC_RED, s);
-  tc::filter_tc_red_kernel<<<grid, 256, tc::kRedSmemBytes, s>>>(R, nblocks);
+  tc::filter_tc_red_kernel<<<grid, tc::kRedThreads, tc::kRedSmemBytes, s>>>(R, nblocks);
   prof_end(K_FILTER_TC_RED, s);
   return cudaGetLastError();
 }
