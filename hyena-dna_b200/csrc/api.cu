@@ -403,7 +403,8 @@ HY_API int hyena_b200_core_bwd(const float* dy_pre, const float* p, const float*
     }
     a.A = c.A;
     static const bool bwd1 = !(getenv("HYENA_B200_ROW_BWD1") && !strcmp(getenv("HYENA_B200_ROW_BWD1"), "0"));
-    HY_CUDA(launch_row_pass((B == 1 && gspec_saved && bwd1) ? ROW_CONV_BWD1 : ROW_CONV_BWD, a, n, s));   // A <- rows of dg, A3 <- rows of dk
+    // (the 128-thread batch-1 kernel exists for 1024-point rows only)
+    HY_CUDA(launch_row_pass((B == 1 && gspec_saved && bwd1 && a.logM2 == 10) ? ROW_CONV_BWD1 : ROW_CONV_BWD, a, n, s));   // A <- rows of dg, A3 <- rows of dk
     a.src = dy_pre; a.src2 = c_saved; a.out2 = ds_scratch; a.red = dfbias; a.dsw = dsw; a.dsb = dsb;
     HY_CUDA(launch_col_inv(INV_BWD_DG, a, n * B, s));
     a.B = 1; a.out = dk;
