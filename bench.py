@@ -56,6 +56,7 @@ def parse():
                     help="sequence length of the bounded CPU sample (cpu_baseline / reference arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="sequence chunks of the HostStep copy pipeline")
     return ap.parse_args()
 
 
@@ -275,7 +276,7 @@ def main():
         y_host = torch.empty(B, L, D).pin_memory()
         du_host = torch.empty(B, L, D).pin_memory()
         g_host = [torch.empty(p.shape).pin_memory() for p in params]
-        hs = H.HostStep(op, B, L, chunks=4)
+        hs = H.HostStep(op, B, L, chunks=args.e2e_chunks)
 
         reduce_fn = H.distributed.allreduce_tensors if world > 1 else None
 
@@ -298,7 +299,7 @@ def main():
         e2e = {"value": world * B * L / (e2e_ms * 1e-3), "unit": "nt/s", "ms_per_step": round(e2e_ms, 3),
                "h2d_bytes_per_step": 2 * B * L * D * 4, "d2h_bytes_per_step": 2 * B * L * D * 4 + pbytes,
                "note": "per GPU, through hyena_dna_b200.HostStep: u,dy pinned host -> device; y, du, param grads device -> "
-                       "pinned host; u uploaded in 4 sequence chunks under the in_proj GEMM slices, dy under the forward, "
+                       f"pinned host; u uploaded in {args.e2e_chunks} sequence chunks under the in_proj GEMM slices, dy under the forward, "
                        "y and du downloaded in chunks under the backward"}
 
     # ---------------- CPU baseline (rank 0, N = 1 only)

@@ -278,7 +278,8 @@ def gemm(transa, transb, m, n, k, A, lda, strideA, B, ldb, strideB, C, ldc, stri
          emulate=True):
     """Column-major strided-batched C = op(A) op(B) + beta*C (+bias) on cuBLASLt 12.9 (see csrc/gemm.cu)."""
     dev = C.device
-    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    # one workspace per (device, stream): GEMMs issued on different streams may run concurrently
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), _stream())
     ws = _gemm_ws.get(key)
     if ws is None:
         ws = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
@@ -288,3 +289,21 @@ def gemm(transa, transb, m, n, k, A, lda, strideA, B, ldb, strideB, C, ldc, stri
                                               _ptr(B), ldb, strideB, float(beta), _ptr(C), ldc, strideC, batch,
                                               _ptr(bias), int(emulate), _ptr(ws), ws.numel(), _stream()))
     return C
+
+
+_side_streams = {}
+
+
+def side_stream(device):
+    """A second stream per device for work that is independent of the main chain (weight-gradient GEMMs run there
+    while the input-gradient GEMM runs on the caller's stream: one op's cuBLASLt input scan overlaps the other's
+    tensor-core phase).  HYENA_B200_SIDE_STREAM=0 disables it."""
+    import os
+    if os.environ.get("HYENA_B200_SIDE_STREAM", "1") == "0":
+        return None
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    s = _side_streams.get(key)
+    if s is None:
+        s = torch.cuda.Stream(device=device)
+        _side_streams[key] = s
+    return s
