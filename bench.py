@@ -264,9 +264,17 @@ def main():
     kernels = {k: {"ms_per_step": round(v[0] / args.steps, 4), "launches_per_step": v[1] / args.steps,
                    "share_of_span": round(v[0] / max(sum(x[0] for x in prof.values()), 1e-9), 4)}
                for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+    traffic, traffic_src = None, None
+    try:     # DRAM bytes of the same kernels from the committed ncu capture (same shape only)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "span_traffic.json")))
+        if (L, D, B) == (L_FULL, D_MODEL, 1):
+            traffic, traffic_src = tj["span_dram_bytes_per_step"], tj["source"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "custom-kernel span (in_proj output -> out_proj input), fwd+bwd, per step",
                 "achieved": round(achieved, 1), "peak": peak_gbs, "unit": "GB/s",
-                "frac": round(achieved / peak_gbs, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(achieved / peak_gbs, 4), "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_step": span_bytes, "span_ms_per_step": round(span_ms, 4),
                 "step_ms": round(ms_step, 4), "kernels": kernels}
 

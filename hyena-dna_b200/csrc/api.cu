@@ -112,12 +112,13 @@ static int pick_log_m2(int logM) {
 static size_t row_bytes(int L) { return ((size_t)1 << log_m_for(L)) * sizeof(float2); }
 
 static size_t group_budget_bytes() {
-  // scratch rows in flight per launch group.  Measured on B200 (profiles/r1_group_sweep.txt): the passes are
-  // issue/latency bound, not HBM bound, so many waves per launch beat keeping the scratch L2-resident
+  // scratch rows in flight per launch group.  Measured on B200 (profiles/r1_config_sweep.txt, two sweeps): with
+  // separate kernels per pass the scratch does not survive in L2 anyway, and many waves per launch win, so the
+  // default lets a whole (B=1, D=256, L=2^20) operator go in one launch per pass
   static size_t v = 0;
   if (!v) {
     const char* e = getenv("HYENA_B200_GROUP_MB");
-    long mb = e ? atol(e) : 512;
+    long mb = e ? atol(e) : 2048;
     if (mb < 1) mb = 1;
     v = (size_t)mb << 20;
   }
