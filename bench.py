@@ -310,6 +310,23 @@ def main():
                        f"pinned host; u uploaded in {args.e2e_chunks} sequence chunks under the in_proj GEMM slices, dy under the forward, "
                        "y and du downloaded in chunks under the backward"}
 
+    # ---------------- informational: the same step with TF32 projections (the reference's training setting,
+    # train.py:34-35; NOT the matched-numerics number, reported separately and never used for `value`)
+    tf32_ms = None
+    if world == 1 and not args.no_e2e:
+        torch.backends.cuda.matmul.allow_tf32 = True
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(args.steps):
+            step()
+        b1.record()
+        torch.cuda.synchronize()
+        tf32_ms = b0.elapsed_time(b1) / args.steps
+        torch.backends.cuda.matmul.allow_tf32 = False
+
     # ---------------- CPU baseline (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -324,6 +341,7 @@ def main():
                            "parallelism": f"dp{world} (batch-sharded replicas, grad all-reduce)",
                            "l2": "inputs larger than L2 (u, p, dy are 1-3 GB each; 126 MB L2), no explicit flush"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "tf32_projections_ms_per_step": tf32_ms,
                 "impl": "b200"}
         print(json.dumps(line), flush=True)
     if world > 1:

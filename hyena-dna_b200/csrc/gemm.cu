@@ -108,8 +108,8 @@ HY_API int hyena_b200_gemm_available(void) {
 }
 
 /* Column-major strided-batched C = alpha * op(A) op(B) + beta * C (+ bias[m] broadcast over columns),
- * fp32 in / fp32 out, computed with CUBLAS_COMPUTE_32F_EMULATED_16BFX9 when emulate != 0 and plain
- * CUBLAS_COMPUTE_32F otherwise.  op = 'N' (0) or 'T' (1).  workspace: >= 32 MiB recommended. */
+ * fp32 in / fp32 out; emulate: 1 = CUBLAS_COMPUTE_32F_EMULATED_16BFX9, 2 = CUBLAS_COMPUTE_32F_FAST_TF32 (only when
+ * the caller opted into TF32), 0 = plain CUBLAS_COMPUTE_32F.  op = 'N' (0) or 'T' (1).  workspace: >= 32 MiB recommended. */
 HY_API int hyena_b200_gemm(int transa, int transb, int m, int n, int k, float alpha, const float* A, int lda,
                            long long strideA, const float* B, int ldb, long long strideB, float beta, float* C,
                            int ldc, long long strideC, int batch, const float* bias, int emulate, void* workspace,
@@ -120,7 +120,9 @@ HY_API int hyena_b200_gemm(int transa, int transb, int m, int n, int k, float al
   Key key{transa, transb, m, n, k, lda, ldb, ldc, batch, strideA, strideB, strideC, bias != nullptr, emulate};
   Plan& p = g_plans[key];
   if (!p.desc) {
-    const cublasComputeType_t ct = emulate ? CUBLAS_COMPUTE_32F_EMULATED_16BFX9 : CUBLAS_COMPUTE_32F;
+    // emulate: 0 = plain fp32, 1 = BF16x9 emulation (fp32-level accuracy), 2 = TF32 (opt-in: torch allow_tf32)
+    const cublasComputeType_t ct = emulate == 1 ? CUBLAS_COMPUTE_32F_EMULATED_16BFX9
+                                   : emulate == 2 ? CUBLAS_COMPUTE_32F_FAST_TF32 : CUBLAS_COMPUTE_32F;
     if (g_lt.DescCreate(&p.desc, ct, CUDA_R_32F) != CUBLAS_STATUS_SUCCESS) return api_fail("cublasLtMatmulDescCreate failed");
     cublasOperation_t ta = transa ? CUBLAS_OP_T : CUBLAS_OP_N, tb = transb ? CUBLAS_OP_T : CUBLAS_OP_N;
     g_lt.DescSet(p.desc, CUBLASLT_MATMUL_DESC_TRANSA, &ta, sizeof(ta));

@@ -275,8 +275,14 @@ def gemm_mode():
 
 
 def gemm(transa, transb, m, n, k, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, batch=1, beta=0.0, bias=None,
-         emulate=True):
-    """Column-major strided-batched C = op(A) op(B) + beta*C (+bias) on cuBLASLt 12.9 (see csrc/gemm.cu)."""
+         emulate=None):
+    """Column-major strided-batched C = op(A) op(B) + beta*C (+bias) on cuBLASLt 12.9 (see csrc/gemm.cu).
+
+    Precision follows PyTorch's own switch, like the reference's nn.Linear does: fp32-accurate BF16x9 emulation by
+    default, TF32 tensor cores when the user set ``torch.backends.cuda.matmul.allow_tf32 = True`` (the reference
+    training script does, train.py:34-35)."""
+    if emulate is None:
+        emulate = 2 if torch.backends.cuda.matmul.allow_tf32 else 1
     dev = C.device
     # one workspace per (device, stream): GEMMs issued on different streams may run concurrently
     key = (dev.index if dev.index is not None else torch.cuda.current_device(), _stream())
