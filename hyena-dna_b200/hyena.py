@@ -133,8 +133,14 @@ class HyenaFilter(OptimModule):
         if bias is None:
             bias = self.bias
         bias = bias if self.use_bias else 0 * bias
+        bias = bias.reshape(-1).to(torch.float32)
+        if x.dim() == 5:        # the reference operator's layout (b, heads, v, blocks, l)  (hyena.py:396-402, :423)
+            b, h, v, z, l = x.shape
+            x3 = x.permute(0, 3, 1, 2, 4).reshape(b * z, h * v, l)
+            y = fftconv_func(x3.to(torch.float32), k, bias, gelu=False)
+            return y.reshape(b, z, h, v, l).permute(0, 2, 3, 1, 4).to(dtype=x.dtype)
         shape = x.shape
-        y = fftconv_func(x.reshape(-1, shape[-2], shape[-1]), k, bias.reshape(-1).to(torch.float32), gelu=False)
+        y = fftconv_func(x.reshape(-1, shape[-2], shape[-1]).to(torch.float32), k, bias, gelu=False)
         return y.reshape(shape).to(dtype=x.dtype)
 
 

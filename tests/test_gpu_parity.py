@@ -345,3 +345,22 @@ def test_baseline_configs_full_size_against_fp32_oracle(name, B, L, D):
     for n in ("filter_fn.bias", "short_filter.weight", "short_filter.bias", "in_proj.weight", "out_proj.weight",
               "filter_fn.implicit_filter.6.weight", "filter_fn.implicit_filter.0.weight"):
         _close(got[n].grad, g_ref[n], f"{name} grad {n}", rtol=3e-3, atol=3e-5)
+
+
+def test_hyena_filter_forward_layouts():
+    """HyenaFilter.forward on (B,D,L) and on the reference operator's 5-D (b,h,v,z,l) layout (hyena.py:396-423)."""
+    import hyena_dna_b200 as H
+    dev = _dev()
+    torch.manual_seed(2)
+    D, L = 12, 700
+    f = H.HyenaFilter(D, emb_dim=5, order=64, seq_len=L, w=10.0, lr_pos_emb=0.0).to(dev)
+    x = torch.randn(2, D, L, device=dev)
+    with torch.no_grad():
+        k = f.filter(L)                                     # (1, L, D) like the reference
+        y3 = f(x, L)
+        y3k = f(x, L, k=k, bias=f.bias)
+        y5 = f(x.reshape(2, 1, D, 1, L), L, k=k[0].transpose(0, 1), bias=f.bias[None, :, None])
+    ref = O.fftconv_ref(x.double().cpu(), k[0].transpose(0, 1).double().cpu(), f.bias.double().cpu())
+    _close(y3, ref, "filter.forward 3-D")
+    _close(y3k, ref, "filter.forward 3-D with k")
+    _close(y5.reshape(2, D, L), ref, "filter.forward 5-D")
