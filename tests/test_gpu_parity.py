@@ -364,3 +364,30 @@ def test_hyena_filter_forward_layouts():
     _close(y3, ref, "filter.forward 3-D")
     _close(y3k, ref, "filter.forward 3-D with k")
     _close(y5.reshape(2, D, L), ref, "filter.forward 5-D")
+
+
+def test_wide_model_filter_paths():
+    """d_model > 256 and not a multiple of 128: output-layer halves, channel chunks and the library fallback of the
+    filter weight-gradient reduction."""
+    import hyena_dna_b200 as H
+    dev = _dev()
+    D, L, E = 320, 1500, 5
+    g = torch.Generator().manual_seed(8)
+    P = O.init_params(D, L, emb_dim=E, w=10.0, generator=g)
+    dk = torch.randn(D, L, generator=g)
+    names = [k for k in P if "implicit_filter" in k]
+    Q = {k: v.double().clone().requires_grad_(k in names) for k, v in P.items()}
+    kref = O.hyena_filter(L, Q)[0].transpose(0, 1)
+    kref.backward(dk.double())
+    f = H.HyenaFilter(D, emb_dim=E, order=64, seq_len=L, w=10.0, lr_pos_emb=0.0).to(dev)
+    sd = {k[len("filter_fn."):]: v for k, v in P.items() if k.startswith("filter_fn.")}
+    for extra in ("implicit_filter.3.freq", "implicit_filter.5.freq"):
+        sd[extra] = sd["implicit_filter.1.freq"]
+    f.load_state_dict(sd)
+    k = f.filter_channel_major(L)
+    k.backward(dk.to(dev))
+    _close(k, kref, "wide filter fwd", scale_abs=False)
+    got = dict(f.named_parameters())
+    for name in names:
+        short = name[len("filter_fn."):]
+        _close(got[short].grad, Q[name].grad, f"wide grad {short}", rtol=2e-3, atol=2e-5)
