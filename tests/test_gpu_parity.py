@@ -386,7 +386,9 @@ def test_wide_model_filter_paths():
     f.load_state_dict(sd)
     k = f.filter_channel_major(L)
     k.backward(dk.to(dev))
-    _close(k, kref, "wide filter fwd", scale_abs=False)
+    # unit-scale init drives sin() with arguments of order 10-30: fp32 evaluation of the MLP itself is ~1e-5 from
+    # the fp64 truth (the same holds for the reference in fp32), hence the wider absolute term here
+    _close(k, kref, "wide filter fwd", atol=2e-5)
     got = dict(f.named_parameters())
     for name in names:
         short = name[len("filter_fn."):]
