@@ -121,6 +121,16 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# ----------------------------------------------------------------------------------------- synthetic inputs
+def nucleotide_activations(B, L, D, seed=2222):
+    """token ids ~ U{7,8,9,10} (A,C,G,T; hg38_char_tokenizer.py:58-67), a 16-row embedding table
+    ~ N(0, 0.02^2) and LayerNorm -> unit-scale rows drawn from four distinct vectors."""
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(7, 11, (B, L), generator=g)
+    table = torch.randn(16, D, generator=g) * 0.02
+    return torch.nn.functional.layer_norm(table[ids], (D,))
+
+
 # ----------------------------------------------------------------------------------------- CPU arm
 def cpu_reference_run(L, D, B, steps, warmup, threads=0):
     """Time the oracle (reference torch.fft path restated, fp32) on the host cores."""
@@ -198,8 +208,7 @@ def main():
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
 
-    L, D, B = args.seqlen, args.d_model, args.batch
-    from oracle import hyena_oracle as O   # only for the synthetic-input recipe and the cpu_baseline leg
+    L, D, B = args.seqlen, args.d_model, args.batch      # (oracle/ is imported by the cpu_baseline leg only)
     torch.manual_seed(1234)
     op = H.HyenaOperator(D, L, order=2, filter_order=64, emb_dim=EMB, w=W_FREQ, lr_pos_emb=0.0)
     # model-realistic init (standalone_hyenadna.py:612-641): Linear weights N(0, 0.02), biases 0
@@ -213,7 +222,7 @@ def main():
         op.out_proj.weight.copy_(torch.randn(D, D, generator=g) * 0.02 / 4.0)
     op = op.to(dev)
     params = [p for p in op.parameters() if p.requires_grad]
-    u_host, _ = O.nucleotide_activations(B, L, D, seed=2222 + rank)
+    u_host = nucleotide_activations(B, L, D, seed=2222 + rank)
     dy_host = torch.randn(B, L, D, generator=torch.Generator().manual_seed(1 + rank))
     u_host, dy_host = u_host.pin_memory(), dy_host.pin_memory()
     u = u_host.to(dev).requires_grad_(True)
