@@ -121,6 +121,29 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# ----------------------------------------------------------------------------------------- per-kernel algorithmic bytes
+def kernel_algorithmic_bytes(B, D, L):
+    """Compulsory HBM bytes per step of each kernel class under the current design (FFT scratch assumed
+    on chip, every HBM tensor read or written once per kernel that needs it), fp32.  Keys = hyena_b200_kind_name()."""
+    n = float(B) * D * L                 # (position, channel) pairs per step
+    f = float(D) * L                     # per-channel (filter-side) pairs
+    return {
+        "col_fwd<gate>": 8 * n,                          # x1, v rows of p
+        "col_fwd<dc>": 8 * n,                            # dy_pre, x0 row of p
+        "col_fwd<filter>": 4 * f,                        # k
+        "row_pass<filter>": 8 * f,                       # kspec out
+        "row_pass<conv_fwd>": 8 * f + 8 * n,             # kspec in, saved g spectrum out
+        "row_pass<conv_bwd>": 8 * f + 8 * n,             # kspec in, saved g spectrum in
+        "col_inv<conv_fwd>": 20 * n,                     # x0,x1,v in; y_pre, c out
+        "col_inv<bwd_dg>": 32 * n,                       # x0,x1,v, dy_pre, c in; ds (3 rows) out
+        "col_inv<dk>": 4 * f,                            # dk out
+        "short_conv_bwd": 24 * n,                        # ds in, dp out
+        "filter_tc_fwd": 4 * f,                          # k out
+        "filter_tc_bwd": 8 * f + 7 * 64 * 4.0 * L,       # dk in, dh out, seven (64, L) arrays out
+        "filter_tc_red": 4 * f + 7 * 64 * 4.0 * L,       # dh and the seven arrays in
+    }
+
+
 # ----------------------------------------------------------------------------------------- synthetic inputs
 def nucleotide_activations(B, L, D, seed=2222):
     """token ids ~ U{7,8,9,10} (A,C,G,T; hg38_char_tokenizer.py:58-67), a 16-row embedding table
@@ -283,9 +306,18 @@ def main():
     span_bytes = (44.0 + 16.0 / B) * D * B * L               # SURVEY.md S8(d), per step
     span_ms = sum(v[0] for v in prof.values()) / args.steps
     achieved = span_bytes / (span_ms * 1e-3) / 1e9 if span_ms > 0 else 0.0
-    kernels = {k: {"ms_per_step": round(v[0] / args.steps, 4), "launches_per_step": v[1] / args.steps,
-                   "share_of_span": round(v[0] / max(sum(x[0] for x in prof.values()), 1e-9), 4)}
-               for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+    kab = kernel_algorithmic_bytes(B, D, L)
+    kernels = {}
+    for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+        ms_k = v[0] / args.steps
+        ent = {"ms_per_step": round(ms_k, 4), "launches_per_step": v[1] / args.steps,
+               "share_of_span": round(v[0] / max(sum(x[0] for x in prof.values()), 1e-9), 4)}
+        if k in kab and ms_k > 0:
+            ent["algorithmic_bytes_per_step"] = kab[k]
+            ent["achieved_gbs"] = round(kab[k] / (ms_k * 1e-3) / 1e9, 1)
+            ent["frac_of_peak"] = round(kab[k] / (ms_k * 1e-3) / 1e9 / peak_gbs, 4)
+        kernels[k] = ent
+    dominant = next(iter(kernels), None)
     traffic, traffic_src = None, None
     try:     # DRAM bytes of the same kernels from the committed ncu capture (same shape only)
         tj = json.load(open(os.path.join(ROOT, "profiles", "span_traffic.json")))
@@ -298,7 +330,9 @@ def main():
                 "frac": round(achieved / peak_gbs, 4), "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_step": span_bytes, "span_ms_per_step": round(span_ms, 4),
-                "step_ms": round(ms_step, 4), "kernels": kernels}
+                "step_ms": round(ms_step, 4),
+                "dominant_kernel": ({"name": dominant, **kernels[dominant]} if dominant else None),
+                "kernels": kernels}
 
     # ---------------- e2e: host buffers in, host buffers out
     e2e = None
