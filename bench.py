@@ -144,6 +144,49 @@ def kernel_algorithmic_bytes(B, D, L):
     }
 
 
+# ----------------------------------------------------------------------------------------- roofline assembly
+def build_roofline(prof, steps, B, D, L, ms_step):
+    """prof: {kernel class: (summed device ms over `steps` steps, launches)} from hyena_dna_b200._lib.profile_end().
+    Pure function (unit-tested on CPU in tests/test_bench_logic.py)."""
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    span_bytes = (44.0 + 16.0 / B) * D * B * L               # SURVEY.md S8(d), per step
+    tot_ms = sum(v[0] for v in prof.values())
+    span_ms = tot_ms / steps
+    achieved = span_bytes / (span_ms * 1e-3) / 1e9 if span_ms > 0 else 0.0
+    kab = kernel_algorithmic_bytes(B, D, L)
+    kernels = {}
+    for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+        ms_k = v[0] / steps
+        ent = {"ms_per_step": round(ms_k, 4), "launches_per_step": v[1] / steps,
+               "share_of_span": round(v[0] / max(tot_ms, 1e-9), 4)}
+        if k in kab and ms_k > 0:
+            ent["algorithmic_bytes_per_step"] = kab[k]
+            ent["achieved_gbs"] = round(kab[k] / (ms_k * 1e-3) / 1e9, 1)
+            ent["frac_of_peak"] = round(kab[k] / (ms_k * 1e-3) / 1e9 / peak_gbs, 4)
+        kernels[k] = ent
+    dominant = next(iter(kernels), None)
+    traffic, traffic_src = None, None
+    try:     # DRAM bytes of the same kernels from the committed ncu capture (same shape only)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "span_traffic.json")))
+        if (L, D, B) == (L_FULL, D_MODEL, 1):
+            traffic, traffic_src = tj["span_dram_bytes_per_step"], tj["source"]
+    except Exception:
+        pass
+    return {"bound": "hbm", "kernel": "custom-kernel span (in_proj output -> out_proj input), fwd+bwd, per step",
+            "achieved": round(achieved, 1), "peak": peak_gbs, "unit": "GB/s",
+            "frac": round(achieved / peak_gbs, 4), "traffic": traffic, "traffic_source": traffic_src,
+            "peak_source": peak_src, "algorithmic_bytes_per_step": span_bytes, "span_ms_per_step": round(span_ms, 4),
+            "step_ms": round(ms_step, 4),
+            "dominant_kernel": ({"name": dominant, **kernels[dominant]} if dominant else None),
+            "kernels": kernels}
+
+
 # ----------------------------------------------------------------------------------------- synthetic inputs
 def nucleotide_activations(B, L, D, seed=2222):
     """token ids ~ U{7,8,9,10} (A,C,G,T; hg38_char_tokenizer.py:58-67), a 16-row embedding table
@@ -296,43 +339,7 @@ def main():
     value = world * B * L / (ms_step * 1e-3)
 
     # ---------------- roofline of the custom-kernel span (rank 0's kernels)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    span_bytes = (44.0 + 16.0 / B) * D * B * L               # SURVEY.md S8(d), per step
-    span_ms = sum(v[0] for v in prof.values()) / args.steps
-    achieved = span_bytes / (span_ms * 1e-3) / 1e9 if span_ms > 0 else 0.0
-    kab = kernel_algorithmic_bytes(B, D, L)
-    kernels = {}
-    for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0]):
-        ms_k = v[0] / args.steps
-        ent = {"ms_per_step": round(ms_k, 4), "launches_per_step": v[1] / args.steps,
-               "share_of_span": round(v[0] / max(sum(x[0] for x in prof.values()), 1e-9), 4)}
-        if k in kab and ms_k > 0:
-            ent["algorithmic_bytes_per_step"] = kab[k]
-            ent["achieved_gbs"] = round(kab[k] / (ms_k * 1e-3) / 1e9, 1)
-            ent["frac_of_peak"] = round(kab[k] / (ms_k * 1e-3) / 1e9 / peak_gbs, 4)
-        kernels[k] = ent
-    dominant = next(iter(kernels), None)
-    traffic, traffic_src = None, None
-    try:     # DRAM bytes of the same kernels from the committed ncu capture (same shape only)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "span_traffic.json")))
-        if (L, D, B) == (L_FULL, D_MODEL, 1):
-            traffic, traffic_src = tj["span_dram_bytes_per_step"], tj["source"]
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": "custom-kernel span (in_proj output -> out_proj input), fwd+bwd, per step",
-                "achieved": round(achieved, 1), "peak": peak_gbs, "unit": "GB/s",
-                "frac": round(achieved / peak_gbs, 4), "traffic": traffic, "traffic_source": traffic_src,
-                "peak_source": peak_src,
-                "algorithmic_bytes_per_step": span_bytes, "span_ms_per_step": round(span_ms, 4),
-                "step_ms": round(ms_step, 4),
-                "dominant_kernel": ({"name": dominant, **kernels[dominant]} if dominant else None),
-                "kernels": kernels}
+    roofline = build_roofline(prof, args.steps, B, D, L, ms_step)
 
     # ---------------- e2e: host buffers in, host buffers out
     e2e = None
