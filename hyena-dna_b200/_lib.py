@@ -97,7 +97,7 @@ def profile_begin():
 
 def profile_end():
     """-> {kernel class: (device ms, launches)} for the window opened by profile_begin()."""
-    n = 20
+    n = 21
     ms = (ctypes.c_double * n)()
     cnt = (ctypes.c_ulonglong * n)()
     check(lib().hyena_b200_profile_end(ms, cnt, n))

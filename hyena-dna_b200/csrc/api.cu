@@ -247,7 +247,7 @@ HY_API const char* hyena_b200_kind_name(int kind) {
       "col_fwd<filter>", "col_fwd<gate>", "col_fwd<dc>", "col_fwd<plain>",
       "col_inv<conv_fwd>", "col_inv<bwd_dg>", "col_inv<dk>", "col_inv<plain_fwd>", "col_inv<plain_bwd>",
       "row_pass<filter>", "row_pass<conv_fwd>", "row_pass<conv_bwd>",
-      "filter_fwd", "filter_bwd", "short_conv_bwd", "twiddle_init", "filter_tc_prep", "filter_tc_fwd", "filter_tc_bwd", "filter_tc_red"};
+      "filter_fwd", "filter_bwd", "short_conv_bwd", "twiddle_init", "filter_tc_prep", "filter_tc_fwd", "filter_tc_bwd", "filter_tc_red", "fused_conv_fwd"};
   return (kind >= 0 && kind < K_COUNT) ? names[kind] : "?";
 }
 
@@ -397,6 +397,18 @@ HY_API int hyena_b200_core_fwd(const float* p, const float* in_bias, const float
   a.gspec = reinterpret_cast<float2*>(gspec_save);
   a.vec = ((L & 1) == 0) && aligned8(p) && aligned8(y_pre) && (!c_save || aligned8(c_save));
   a.stage = ((L & 3) == 0) && aligned16(p) && !getenv("HYENA_B200_NO_STAGE");
+  // Experimental single cooperative kernel (pass 1 -> grid.sync -> pass 2 -> grid.sync -> pass 3 per L2-sized row
+  // group, csrc/fused_conv.cuh): HYENA_B200_FUSED=1, group budget HYENA_B200_FUSED_MB (default 64)
+  static const bool fused = getenv("HYENA_B200_FUSED") && !strcmp(getenv("HYENA_B200_FUSED"), "1");
+  if (fused && a.logM2 == 10 && a.logM1 >= 5) {
+    static const long fmb = getenv("HYENA_B200_FUSED_MB") ? atol(getenv("HYENA_B200_FUSED_MB")) : 64;
+    size_t per_ch = row_bytes(L) * (size_t)B;
+    int cpg = (int)(((size_t)(fmb < 1 ? 1 : fmb) << 20) / per_ch);
+    if (cpg < 1) cpg = 1;
+    if (cpg > c.nch) cpg = c.nch;
+    HY_CUDA(launch_fused_conv_fwd(a, D, cpg, s));
+    return 0;
+  }
   for (int c0 = 0; c0 < D; c0 += c.nch) {
     const int n = (D - c0 < c.nch) ? D - c0 : c.nch;
     a.c0 = c0;

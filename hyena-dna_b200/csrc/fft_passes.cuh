@@ -239,18 +239,19 @@ __device__ __forceinline__ float2 col_input(const PassArgs& a, int b, int c, int
 // pass 1: forward column FFT with the input side fused in
 // grid (CTAS, rows); block ColGeo::THREADS
 // ------------------------------------------------------------------------------------------------
+// body of pass 1 for the column tile `bx` of row `by` (the __global__ wrapper passes blockIdx; the fused
+// cooperative kernel loops over tiles)
 template <int LOGM1, int LOGM2, int MODE>
-__global__ void __launch_bounds__(ColGeo<LOGM1, LOGM2>::THREADS, ColGeo<LOGM1, LOGM2>::TWO ? 2 : 1)
-col_fwd_kernel(const PassArgs a) {
+__device__ __forceinline__ void col_fwd_body(const PassArgs& a, const int bx, const int by, unsigned char* smem_raw,
+                                             const int c0x = 0) {
   using CG = ColGeo<LOGM1, LOGM2>;
   constexpr int M1 = CG::M1;
   constexpr int kM2 = CG::M2;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* smem = reinterpret_cast<float2*>(smem_raw);
 
-  const int r = blockIdx.y;
-  const int ci = r / a.B, b = r - ci * a.B, c = a.c0 + ci;
-  const int colbase = blockIdx.x * CG::C;
+  const int r = by;
+  const int ci = r / a.B, b = r - ci * a.B, c = a.c0 + c0x + ci;
+  const int colbase = bx * CG::C;
   const int L = a.L;
   const bool vec = a.vec != 0;
   constexpr int logM = LOGM1 + LOGM2;
@@ -353,6 +354,13 @@ col_fwd_kernel(const PassArgs a) {
   }
 }
 
+template <int LOGM1, int LOGM2, int MODE>
+__global__ void __launch_bounds__(ColGeo<LOGM1, LOGM2>::THREADS, ColGeo<LOGM1, LOGM2>::TWO ? 2 : 1)
+col_fwd_kernel(const PassArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  col_fwd_body<LOGM1, LOGM2, MODE>(a, blockIdx.x, blockIdx.y, smem_raw);
+}
+
 // ------------------------------------------------------------------------------------------------
 // pass 3: inverse column FFT with the output side fused in
 // ------------------------------------------------------------------------------------------------
@@ -443,17 +451,16 @@ __device__ __forceinline__ void inv_output(const PassArgs& a, InvCtx& cx, int b,
 }
 
 template <int LOGM1, int LOGM2, int MODE>
-__global__ void __launch_bounds__(ColGeo<LOGM1, LOGM2>::THREADS, ColGeo<LOGM1, LOGM2>::TWO ? 2 : 1)
-col_inv_kernel(const PassArgs a) {
+__device__ __forceinline__ void col_inv_body(const PassArgs& a, const int bx, const int by, unsigned char* smem_raw,
+                                             const int c0x = 0) {
   using CG = ColGeo<LOGM1, LOGM2>;
   constexpr int M1 = CG::M1;
   constexpr int kM2 = CG::M2;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* smem = reinterpret_cast<float2*>(smem_raw);
 
-  const int r = blockIdx.y;
-  const int ci = r / a.B, b = r - ci * a.B, c = a.c0 + ci;
-  const int colbase = blockIdx.x * CG::C;
+  const int r = by;
+  const int ci = r / a.B, b = r - ci * a.B, c = a.c0 + c0x + ci;
+  const int colbase = bx * CG::C;
   const int L = a.L;
   const bool vec = a.vec != 0;
   const float2* Arow = (MODE == INV_DK ? a.A3 : a.A) + (size_t)r * ((size_t)M1 * kM2);
@@ -616,6 +623,13 @@ col_inv_kernel(const PassArgs a) {
   }
 }
 
+template <int LOGM1, int LOGM2, int MODE>
+__global__ void __launch_bounds__(ColGeo<LOGM1, LOGM2>::THREADS, ColGeo<LOGM1, LOGM2>::TWO ? 2 : 1)
+col_inv_kernel(const PassArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  col_inv_body<LOGM1, LOGM2, MODE>(a, blockIdx.x, blockIdx.y, smem_raw);
+}
+
 // ------------------------------------------------------------------------------------------------
 // pass 2: row FFTs + pointwise spectrum product + inverse row FFTs
 // A row of M2 = 2^LOGM2 points is owned by TPR = M2/32 threads (one warp for 1024, four for 4096);
@@ -732,17 +746,16 @@ __host__ __device__ constexpr size_t row_smem_elems(int rows) {
 // accumulator across the batch, so it fits 128 threads x <= 170 registers and three 4-row CTAs per SM instead of one
 // 8-row CTA at 255 registers (the dc spectrum stays in shared memory between the two pointwise/inverse phases).
 template <int MODE, int LOGM2>
-__global__ void __launch_bounds__(MODE == ROW_CONV_BWD1 ? 128 : 256, MODE == ROW_CONV_BWD ? 1 : (MODE == ROW_CONV_BWD1 ? 3 : 2))
-row_pass_kernel(const PassArgs a) {
+__device__ __forceinline__ void row_pass_body(const PassArgs& a, const int bx, const int by, unsigned char* smem_raw,
+                                              const int c0x = 0) {
   using RG = RowGeo<LOGM2>;
   constexpr int M2 = RG::M2, TPR = RG::TPR;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* smem = reinterpret_cast<float2*>(smem_raw);
   const int M1 = 1 << a.logM1;
   const int logM = a.logM1 + LOGM2;
   const int slot = threadIdx.x / TPR, q = threadIdx.x % TPR;
   const int nslots = blockDim.x / TPR;
-  const RowIds id = row_ids(M1, nslots, blockIdx.x, slot);
+  const RowIds id = row_ids(M1, nslots, bx, slot);
   const size_t rowElems = (size_t)M1 * M2;
   const RowSync<LOGM2> rsync{1 + slot};
 
@@ -752,8 +765,8 @@ row_pass_kernel(const PassArgs a) {
   float2* zbufp = smem + nslots * RG::EX + id.pslot * M2;
 
   if constexpr (MODE == ROW_FILTER) {
-    const int c = a.c0 + blockIdx.y;
-    const float2* src = a.A + (size_t)blockIdx.y * rowElems + (size_t)id.k1 * M2;
+    const int c = a.c0 + c0x + by;
+    const float2* src = a.A + (size_t)by * rowElems + (size_t)id.k1 * M2;
     float2* dst = a.kspec_out + (size_t)c * rowElems + (size_t)id.k1 * M2;
     float2 v[32];
     static_for<0, 32>([&](auto n_) { constexpr int n1 = decltype(n_)::value; v[n1] = src[TPR * n1 + q]; });
@@ -768,14 +781,14 @@ row_pass_kernel(const PassArgs a) {
     const float2 wbase = cmul(root20(a.T, (uint32_t)id.k1 << (20 - logM)), root20(a.T, (uint32_t)q << (20 - LOGM2)));
 
     if constexpr (MODE == ROW_CONV_FWD) {
-      const int r = blockIdx.y;
-      const int ci = r / a.B, c = a.c0 + ci;
+      const int r = by;
+      const int ci = r / a.B, c = a.c0 + c0x + ci;
       float2* Arow = a.A + (size_t)r * rowElems + (size_t)id.k1 * M2;
       const float2* Krow = a.kspec + (size_t)c * rowElems + (size_t)id.k1 * M2;
       const float2* Kprow = a.kspec + (size_t)c * rowElems + (size_t)id.pk1 * M2;
       row_fft_to_smem<LOGM2>(Arow, ex, ex, q, a.T, rsync);
       if (a.gspec) {                                    // keep the spectrum of g for the backward pass
-        float2* G = a.gspec + ((size_t)ci * a.B + (r - ci * a.B) + (size_t)a.c0 * a.B) * rowElems + (size_t)id.k1 * M2;
+        float2* G = a.gspec + ((size_t)ci * a.B + (r - ci * a.B) + (size_t)(a.c0 + c0x) * a.B) * rowElems + (size_t)id.k1 * M2;
         static_for<0, 32>([&](auto s_) { constexpr int s = decltype(s_)::value; G[TPR * s + q] = ex[TPR * s + q]; });
       }
       __syncthreads();
@@ -795,7 +808,7 @@ row_pass_kernel(const PassArgs a) {
       __syncthreads();                                  // partner rows are done reading this row's spectrum
       row_ifft_store<LOGM2>(v, ex, Arow, q, id.k1, logM, a.T, rsync);
     } else if constexpr (MODE == ROW_CONV_BWD1) {
-      const int ci = blockIdx.y, c = a.c0 + ci;          // B == 1: row index == channel index of the group
+      const int ci = by, c = a.c0 + c0x + ci;            // B == 1: row index == channel index of the group
       const float2* Krow = a.kspec + (size_t)c * rowElems + (size_t)id.k1 * M2;
       const float2* Kprow = a.kspec + (size_t)c * rowElems + (size_t)id.pk1 * M2;
       const float2* Grow = a.gspec + (size_t)c * rowElems + (size_t)id.k1 * M2;
@@ -834,7 +847,7 @@ row_pass_kernel(const PassArgs a) {
       float2* Krow_out = a.A3 + (size_t)ci * rowElems + (size_t)id.k1 * M2;
       row_ifft_store<LOGM2>(v, ex, Krow_out, q, id.k1, logM, a.T, rsync);
     } else {   // ROW_CONV_BWD: loop over the batch, accumulate dK' in registers
-      const int ci = blockIdx.y, c = a.c0 + ci;
+      const int ci = by, c = a.c0 + c0x + ci;
       const float2* Krow = a.kspec + (size_t)c * rowElems + (size_t)id.k1 * M2;
       const float2* Kprow = a.kspec + (size_t)c * rowElems + (size_t)id.pk1 * M2;
       float2 acc[32];
@@ -846,7 +859,7 @@ row_pass_kernel(const PassArgs a) {
         row_fft_to_smem<LOGM2>(Drow, ex, zbuf, q, a.T, rsync);     // dc spectrum -> zbuf
         rsync();
         if (a.gspec) {                                             // saved by the forward pass: just load it
-          const float2* G = a.gspec + ((size_t)(a.c0 + ci) * a.B + b) * rowElems + (size_t)id.k1 * M2;
+          const float2* G = a.gspec + ((size_t)(a.c0 + c0x + ci) * a.B + b) * rowElems + (size_t)id.k1 * M2;
           static_for<0, 32>([&](auto s_) { constexpr int s = decltype(s_)::value; ex[TPR * s + q] = __ldg(G + TPR * s + q); });
         } else {
           row_fft_to_smem<LOGM2>(Grow, ex, ex, q, a.T, rsync);     // g spectrum  -> the exchange area itself
@@ -880,6 +893,13 @@ row_pass_kernel(const PassArgs a) {
       row_ifft_store<LOGM2>(acc, ex, Krow_out, q, id.k1, logM, a.T, rsync);
     }
   }
+}
+
+template <int MODE, int LOGM2>
+__global__ void __launch_bounds__(MODE == ROW_CONV_BWD1 ? 128 : 256, MODE == ROW_CONV_BWD ? 1 : (MODE == ROW_CONV_BWD1 ? 3 : 2))
+row_pass_kernel(const PassArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  row_pass_body<MODE, LOGM2>(a, blockIdx.x, blockIdx.y, smem_raw);
 }
 
 }  // namespace hy

@@ -12,13 +12,14 @@ enum Kind {
   K_COL_INV = 4,      // + InvMode  (4..8)
   K_ROW = 9,          // + RowMode  (9..11)
   K_FILTER_FWD = 12, K_FILTER_BWD = 13, K_SHORT_BWD = 14, K_TWIDDLE = 15, K_FILTER_TC_PREP = 16, K_FILTER_TC_FWD = 17,
-  K_FILTER_TC_BWD = 18, K_FILTER_TC_RED = 19, K_COUNT = 20
+  K_FILTER_TC_BWD = 18, K_FILTER_TC_RED = 19, K_FUSED_FWD = 20, K_COUNT = 21
 };
 void prof_begin(int kind, cudaStream_t s);     // api.cu: records an event when profiling is on
 void prof_end(int kind, cudaStream_t s);       // api.cu: records an event when profiling is on; counts the launch
 cudaError_t launch_col_fwd(int mode, const PassArgs& a, int rows, cudaStream_t s);
 cudaError_t launch_col_inv(int mode, const PassArgs& a, int rows, cudaStream_t s);
 cudaError_t launch_row_pass(int mode, const PassArgs& a, int rows, cudaStream_t s);
+cudaError_t launch_fused_conv_fwd(const PassArgs& a, int channels, int ch_per_group, cudaStream_t s);   // k_fused.cu
 cudaError_t launch_filter_fwd(const FilterParams& P, float* kout, cudaStream_t s);
 cudaError_t launch_filter_fwd_tc(const FilterParams& P, float* wimg, float* kout, cudaStream_t s);   // k_filter_tc.cu
 size_t filter_tc_wimg_bytes(int D);
