@@ -284,6 +284,23 @@ static int get_wimg(int D, cudaStream_t stream, float** out) {
   return 0;
 }
 
+// dataflow fused conv (HYENA_B200_FUSED=2): per-device completion counters (grow-only)
+static int get_flow_counters(size_t n_ints, cudaStream_t stream, int** out) {
+  int dev = -1;
+  HY_CUDA(cudaGetDevice(&dev));
+  HY_CHECK(dev >= 0 && dev < 64, "unsupported device ordinal %d", dev);
+  std::lock_guard<std::mutex> lk(g_mu);
+  static int* bufs[64] = {nullptr};
+  static size_t sizes[64] = {0};
+  if (sizes[dev] < n_ints) {
+    if (bufs[dev]) { HY_CUDA(cudaStreamSynchronize(stream)); HY_CUDA(cudaFree(bufs[dev])); }
+    HY_CUDA(cudaMalloc(&bufs[dev], n_ints * sizeof(int)));
+    sizes[dev] = n_ints;
+  }
+  *out = bufs[dev];
+  return 0;
+}
+
 static int fill_filter_params(FilterParams* P, const float* z, int z_stride, const float* t, const float* W0,
                               const float* b0, const float* W1, const float* b1, const float* W2, const float* b2,
                               const float* W3, const float* freq, const float* deltas, float shift, int modulate,
@@ -397,10 +414,12 @@ HY_API int hyena_b200_core_fwd(const float* p, const float* in_bias, const float
   a.gspec = reinterpret_cast<float2*>(gspec_save);
   a.vec = ((L & 1) == 0) && aligned8(p) && aligned8(y_pre) && (!c_save || aligned8(c_save));
   a.stage = ((L & 3) == 0) && aligned16(p) && !getenv("HYENA_B200_NO_STAGE");
-  // Experimental single cooperative kernel (pass 1 -> grid.sync -> pass 2 -> grid.sync -> pass 3 per L2-sized row
-  // group, csrc/fused_conv.cuh): HYENA_B200_FUSED=1, group budget HYENA_B200_FUSED_MB (default 64)
-  static const bool fused = getenv("HYENA_B200_FUSED") && !strcmp(getenv("HYENA_B200_FUSED"), "1");
-  if (fused && a.logM2 == 10 && a.logM1 >= 5) {
+  // Experimental one-kernel forms of the three passes (csrc/fused_conv.cuh), both off by default:
+  //   HYENA_B200_FUSED=1  pass 1 -> grid.sync -> pass 2 -> grid.sync -> pass 3 per row group of HYENA_B200_FUSED_MB (64)
+  //   HYENA_B200_FUSED=2  dataflow: per-row completion counters instead of grid barriers, scratch ring of
+  //                       2*HYENA_B200_FLOW_DIST+2 rows (default DIST 2)
+  static const int fused = getenv("HYENA_B200_FUSED") ? atoi(getenv("HYENA_B200_FUSED")) : 0;
+  if (fused == 1 && a.logM2 == 10 && a.logM1 >= 5) {
     static const long fmb = getenv("HYENA_B200_FUSED_MB") ? atol(getenv("HYENA_B200_FUSED_MB")) : 64;
     size_t per_ch = row_bytes(L) * (size_t)B;
     int cpg = (int)(((size_t)(fmb < 1 ? 1 : fmb) << 20) / per_ch);
@@ -408,6 +427,17 @@ HY_API int hyena_b200_core_fwd(const float* p, const float* in_bias, const float
     if (cpg > c.nch) cpg = c.nch;
     HY_CUDA(launch_fused_conv_fwd(a, D, cpg, s));
     return 0;
+  }
+  if (fused == 2 && a.logM2 == 10 && a.logM1 >= 5) {
+    static const int dist_env = getenv("HYENA_B200_FLOW_DIST") ? atoi(getenv("HYENA_B200_FLOW_DIST")) : 2;
+    const int dist = dist_env < 1 ? 1 : (dist_env > 8 ? 8 : dist_env);
+    // the ring is indexed by slot * B + batch: it needs (2*dist+2) * B scratch rows; c.A holds c.nch * B
+    if (2 * dist + 2 <= c.nch) {
+      int* counters = nullptr;
+      if (get_flow_counters(3 * (size_t)B * D + 1, s, &counters)) return 1;
+      HY_CUDA(launch_flow_conv_fwd(a, B * D, dist, counters, s));
+      return 0;
+    }
   }
   for (int c0 = 0; c0 < D; c0 += c.nch) {
     const int n = (D - c0 < c.nch) ? D - c0 : c.nch;

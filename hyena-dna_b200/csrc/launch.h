@@ -20,6 +20,7 @@ cudaError_t launch_col_fwd(int mode, const PassArgs& a, int rows, cudaStream_t s
 cudaError_t launch_col_inv(int mode, const PassArgs& a, int rows, cudaStream_t s);
 cudaError_t launch_row_pass(int mode, const PassArgs& a, int rows, cudaStream_t s);
 cudaError_t launch_fused_conv_fwd(const PassArgs& a, int channels, int ch_per_group, cudaStream_t s);   // k_fused.cu
+cudaError_t launch_flow_conv_fwd(const PassArgs& a, int rows, int dist, int* counters, cudaStream_t s);     // k_fused.cu
 cudaError_t launch_filter_fwd(const FilterParams& P, float* kout, cudaStream_t s);
 cudaError_t launch_filter_fwd_tc(const FilterParams& P, float* wimg, float* kout, cudaStream_t s);   // k_filter_tc.cu
 size_t filter_tc_wimg_bytes(int D);
