@@ -1,5 +1,16 @@
+#include <cstdlib>
+
 #include "launch.h"
 namespace hy {
+
+// The batch-1 backward kernel at two CTAs per SM (up to 255 registers, no spills) instead of row_pass_kernel's three CTAs
+// at <= 170 registers with ~80 registers spilled: same body, 3.52 ms instead of 3.94-4.00 ms at large-1m
+// (profiles/r1_config_sweep.txt).  Default; HYENA_B200_ROW_BWD1_CTAS=3 selects the three-CTA form.
+template <int LOGM2>
+__global__ void __launch_bounds__(128, 2) row_pass_bwd1_2cta_kernel(const PassArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  row_pass_body<ROW_CONV_BWD1, LOGM2>(a, blockIdx.x, blockIdx.y, smem_raw);
+}
 
 template <int MODE, int LOGM2>
 static cudaError_t go(const PassArgs& a, int rows, cudaStream_t s) {
@@ -10,6 +21,10 @@ static cudaError_t go(const PassArgs& a, int rows, cudaStream_t s) {
   const int ctas = M1 < rows_cta ? 1 : M1 / rows_cta;
   const size_t smem = row_smem_elems<MODE, LOGM2>(nslots) * sizeof(float2);
   auto kern = row_pass_kernel<MODE, LOGM2>;
+  if constexpr (MODE == ROW_CONV_BWD1) {
+    static const bool three = getenv("HYENA_B200_ROW_BWD1_CTAS") && atoi(getenv("HYENA_B200_ROW_BWD1_CTAS")) == 3;
+    if (!three) kern = row_pass_bwd1_2cta_kernel<LOGM2>;
+  }
   cudaError_t e = set_smem(kern, smem);
   if (e != cudaSuccess) return e;
   prof_begin(K_ROW + (MODE == ROW_CONV_BWD1 ? (int)ROW_CONV_BWD : MODE), s);
