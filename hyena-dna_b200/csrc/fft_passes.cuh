@@ -895,6 +895,88 @@ __device__ __forceinline__ void row_pass_body(const PassArgs& a, const int bx, c
   }
 }
 
+// ROW_CONV_BWD1 with the filter spectrum row and then the saved g spectrum row staged through shared memory by cp.async
+// (issued before the forward row FFT / before the first inverse FFT, so the 2 x 64 dependent __ldg's per thread of the
+// two pointwise phases -- `long_scoreboard`, the top stall of the kernel -- become shared-memory reads).  One 8 KB
+// buffer per row, reused for k then g; the partner row's buffer supplies the mirrored bins.  Shared memory per CTA:
+// rows * (EX + 2 * M2) complex = 99 KB for four rows, two CTAs per SM.  Experimental: HYENA_B200_ROW_BWD1_STAGE=1.
+template <int LOGM2>
+__host__ __device__ constexpr size_t row_bwd1_staged_smem_elems(int rows) {
+  return (size_t)rows * (RowGeo<LOGM2>::EX + 2 * RowGeo<LOGM2>::M2);
+}
+
+template <int LOGM2>
+__device__ __forceinline__ void row_bwd1_staged_body(const PassArgs& a, const int bx, const int by, unsigned char* smem_raw) {
+  using RG = RowGeo<LOGM2>;
+  constexpr int M2 = RG::M2, TPR = RG::TPR;
+  static_assert(LOGM2 == 10, "one warp per row");
+  float2* smem = reinterpret_cast<float2*>(smem_raw);
+  const int M1 = 1 << a.logM1;
+  const int logM = a.logM1 + LOGM2;
+  const int slot = threadIdx.x / TPR, q = threadIdx.x % TPR;
+  const int nslots = blockDim.x / TPR;
+  const RowIds id = row_ids(M1, nslots, bx, slot);
+  const size_t rowElems = (size_t)M1 * M2;
+  const RowSync<LOGM2> rsync{1 + slot};
+
+  float2* ex = smem + slot * RG::EX;
+  float2* zbuf = smem + nslots * RG::EX + slot * M2;
+  float2* zbufp = smem + nslots * RG::EX + id.pslot * M2;
+  float2* kg = smem + nslots * (RG::EX + M2) + slot * M2;            // staged k row, later staged g row
+  const float2* kgp = smem + nslots * (RG::EX + M2) + id.pslot * M2;
+
+  const int ci = by, c = a.c0 + ci;                                  // B == 1
+  const float2* Krow = a.kspec + (size_t)c * rowElems + (size_t)id.k1 * M2;
+  const float2* Grow = a.gspec + (size_t)c * rowElems + (size_t)id.k1 * M2;
+  float2* Drow = a.A + (size_t)ci * rowElems + (size_t)id.k1 * M2;
+  auto stage_row = [&](const float2* src) {                          // 8 KB = 512 x 16 B, 16 per lane, coalesced
+#pragma unroll
+    for (int i = 0; i < M2 / 2 / TPR; ++i) {
+      const int e = 2 * (TPR * i + q);
+      cp_async16(kg + e, src + e, true);
+    }
+    cp_async_commit();
+  };
+  const float2 wbase = cmul(root20(a.T, (uint32_t)id.k1 << (20 - logM)), root20(a.T, (uint32_t)q << (20 - LOGM2)));
+
+  stage_row(Krow);                                                   // in flight under the forward FFT
+  row_fft_to_smem<LOGM2>(Drow, ex, zbuf, q, a.T, rsync);             // dc spectrum -> zbuf (kept for both phases)
+  cp_async_wait_group<0>();
+  __syncthreads();                                                   // own + partner: dc spectrum and k row visible
+  float2 v[32];
+  static_for<0, 32>([&](auto s_) {                                   // phase 1: dg spectrum = corr(dc, k)
+    constexpr int s = decltype(s_)::value;
+    const int k2 = TPR * s + q;
+    const int pc = (M2 - k2 - id.nz) & (M2 - 1);
+    float2 E, O, He, Ho;
+    even_odd(zbuf[k2], cconj(zbufp[pc]), E, O);
+    even_odd(kg[k2], cconj(kgp[pc]), He, Ho);
+    const float2 WE = cmulc(E, mul_w32<s, false>(wbase));
+    float2 Ye = cadd(cmulc(E, He), cmulc(O, Ho));
+    float2 Yo = cadd(cmulc(WE, Ho), cmulc(O, He));
+    v[s] = cadd(Ye, cmul_i(Yo));
+  });
+  __syncthreads();                                                   // the partner is done with this row's k
+  stage_row(Grow);                                                   // in flight under the first inverse FFT
+  row_ifft_store<LOGM2>(v, ex, Drow, q, id.k1, logM, a.T, rsync);
+  cp_async_wait_group<0>();
+  __syncthreads();                                                   // own + partner g rows visible
+  static_for<0, 32>([&](auto s_) {                                   // phase 2: dk spectrum = corr(dc, g)
+    constexpr int s = decltype(s_)::value;
+    const int k2 = TPR * s + q;
+    const int pc = (M2 - k2 - id.nz) & (M2 - 1);
+    float2 E, O, Ge, Go;
+    even_odd(zbuf[k2], cconj(zbufp[pc]), E, O);
+    even_odd(kg[k2], cconj(kgp[pc]), Ge, Go);
+    const float2 WE = cmulc(E, mul_w32<s, false>(wbase));
+    float2 Ke = cadd(cmulc(E, Ge), cmulc(O, Go));
+    float2 Ko = cadd(cmulc(WE, Go), cmulc(O, Ge));
+    v[s] = cadd(Ke, cmul_i(Ko));
+  });
+  float2* Krow_out = a.A3 + (size_t)ci * rowElems + (size_t)id.k1 * M2;
+  row_ifft_store<LOGM2>(v, ex, Krow_out, q, id.k1, logM, a.T, rsync);
+}
+
 template <int MODE, int LOGM2>
 __global__ void __launch_bounds__(MODE == ROW_CONV_BWD1 ? 128 : 256, MODE == ROW_CONV_BWD ? 1 : (MODE == ROW_CONV_BWD1 ? 3 : 2))
 row_pass_kernel(const PassArgs a) {
