@@ -26,5 +26,7 @@ PY
 run default          HYENA_B200_NOOP=1
 run bwd1_3cta        HYENA_B200_ROW_BWD1_CTAS=3
 run bwd1_staged      HYENA_B200_ROW_BWD1_STAGE=1
+run fwd_staged       HYENA_B200_ROW_FWD_STAGE=1
+run both_staged      HYENA_B200_ROW_BWD1_STAGE=1 HYENA_B200_ROW_FWD_STAGE=1
 run fused_coop       HYENA_B200_FUSED=1 HYENA_B200_FUSED_MB=2048
 run fused_flow       HYENA_B200_FUSED=2
