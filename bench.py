@@ -53,7 +53,12 @@ def parse():
                     help="host threads for the CPU arm (0 = min(cores, 16): torch CPU ops were ~40x SLOWER with all "
                          "128 hardware threads of the B200 host than the survey box was with 8)")
     ap.add_argument("--cpu-sample-len", type=int, default=1 << 17,
-                    help="sequence length of the bounded CPU sample (cpu_baseline / reference arm)")
+                    help="sequence length of the bounded CPU sample of the product arm's cpu_baseline leg")
+    ap.add_argument("--ref-seconds", type=float, default=200.0,
+                    help="time budget of the --impl reference arm: it runs the FULL workload (same L, D, batch) and "
+                         "times as many of the requested steps as fit in this budget (at least one)")
+    ap.add_argument("--no-gpu-reference", action="store_true",
+                    help="skip the gpu_reference leg (the reference's torch.fft/cuFFT path timed on the same GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="sequence chunks of the HostStep copy pipeline")
@@ -198,8 +203,9 @@ def nucleotide_activations(B, L, D, seed=2222):
 
 
 # ----------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_run(L, D, B, steps, warmup, threads=0):
-    """Time the oracle (reference torch.fft path restated, fp32) on the host cores."""
+def cpu_reference_run(L, D, B, steps, warmup, threads=0, budget_s=None):
+    """Time the oracle (reference torch.fft path restated, fp32) on the host cores.  With ``budget_s`` the number of
+    timed steps is cut so that the whole call ends within the budget (at least one timed step)."""
     from oracle import hyena_oracle as O
     cores = threads if threads > 0 else min(os.cpu_count() or 1, 16)
     torch.set_num_threads(cores)
@@ -207,37 +213,109 @@ def cpu_reference_run(L, D, B, steps, warmup, threads=0):
     P = O.init_params(D, L, emb_dim=EMB, w=W_FREQ, generator=g, init_std=0.02)
     u, _ = O.nucleotide_activations(B, L, D)
     dy = torch.randn(B, L, D, generator=g)
+    t_start = time.perf_counter()
     tw = time.perf_counter()
     for _ in range(warmup):
         O.operator_fwd_bwd(u, P, dy)
     tw = (time.perf_counter() - tw) / max(warmup, 1)
-    if warmup and tw > 30.0:          # pathologically slow host: do not burn minutes, report the warm-up step
-        steps, dt = 0, tw
-    else:
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            O.operator_fwd_bwd(u, P, dy)
-        dt = (time.perf_counter() - t0) / max(steps, 1)
+    done, t0 = 0, time.perf_counter()
+    for _ in range(max(steps, 1)):
+        O.operator_fwd_bwd(u, P, dy)
+        done += 1
+        per = (time.perf_counter() - t0) / done
+        if budget_s is not None and (time.perf_counter() - t_start) + per > budget_s:
+            break
+    dt = (time.perf_counter() - t0) / done
     return {"value": B * L / dt, "unit": "nt/s", "cores": cores, "kind": "port",
-            "sample": f"oracle fwd+bwd, fp32 torch CPU, B={B} L={L} D={D}, {steps} step(s) after {warmup} warm-up "
-                      f"({dt:.2f} s/step)"}, dt
+            "host_cpus": os.cpu_count(),
+            "sample": f"oracle fwd+bwd, fp32 torch CPU ({cores} threads of {os.cpu_count()} host CPUs), B={B} L={L} "
+                      f"D={D}, {done} timed step(s) after {warmup} warm-up ({dt:.2f} s/step)"}, dt, done
+
+
+def workload_config(L, D, B, world):
+    return {"workload": f"large-1m: HyenaOperator fwd+bwd, L={L} d_model={D} order=2 filter_order=64 "
+                        f"emb_dim={EMB}, batch {B}/GPU (global {world * B}), fp32, TF32 off",
+            "parallelism": f"dp{world} (batch-sharded replicas, grad all-reduce)",
+            "l2": "inputs larger than L2 (u, p, dy are 1-3 GB each; 126 MB L2), no explicit flush"}
 
 
 def reference_arm(args):
+    """The reference's own CPU path (oracle port of the torch.fft path) on the host cores, on the SAME workload
+    (full L, D, batch).  One rank only; under torchrun the other ranks exit without work."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    Ls = min(args.cpu_sample_len, args.seqlen)
-    cb, dt = cpu_reference_run(Ls, args.d_model, 1, args.steps, min(args.warmup, 1), args.cpu_threads)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    L, D, B = args.seqlen, args.d_model, args.batch
+    wu = min(args.warmup, 1)
+    cb, dt, done = cpu_reference_run(L, D, B, args.steps, wu, args.cpu_threads, budget_s=args.ref_seconds)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "nt/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"large-1m HyenaOperator fwd+bwd, bounded CPU sample L={Ls} d_model={args.d_model} "
-                                   f"batch=1 (per-nt cost of the full L=1,048,576 is ~log-factor higher)",
-                       "l2": "n/a (CPU)"},
+            "steps": done, "steps_requested": args.steps, "warmup": wu, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(L, D, B, world),
+            "note": f"ONE host process on {cb['cores']} threads runs one sample of the workload per step regardless of "
+                    f"--gpus (at N>1 the ratio to the N-GPU arm is not a per-GPU anchor); steps cut to the "
+                    f"--ref-seconds budget ({args.ref_seconds:.0f} s)",
             "cpu_baseline": cb, "gpu_launches": 0,
             "e2e": {"value": cb["value"], "unit": "nt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------- reference GPU path
+def gpu_reference_run(op, u, dy, steps=3, warmup=1):
+    """The reference's own GPU path (plain torch ops: F.linear, F.conv1d, torch.fft -> cuFFT; hyena.py:388-444) on the
+    same device, same weights, same inputs, fp32 with TF32 off: the >=10x denominator of north_star.  Imports the
+    UNMODIFIED reference module when /root/reference exists (build container), else runs the oracle restatement of it
+    on cuda (the GPU box has no /root/reference)."""
+    import gc
+    dev = u.device
+    sd = {k: v.detach() for k, v in op.state_dict().items()}
+    B, L, D = u.shape
+    which = None
+    ref_dir = "/root/reference"
+    mod = None
+    if os.path.isdir(ref_dir):
+        try:
+            sys.path.insert(0, ref_dir)
+            import standalone_hyenadna as S
+            mod = S.HyenaOperator(D, L, order=2, filter_order=64, emb_dim=EMB, w=W_FREQ, lr_pos_emb=0.0,
+                                  modulate=True, shift=0.0).to(dev)
+            mod.load_state_dict(sd, strict=True)
+            which = "unmodified /root/reference/standalone_hyenadna.HyenaOperator on cuda"
+        except Exception as e:      # pragma: no cover
+            mod, which = None, None
+            sys.stderr.write(f"gpu_reference: reference import failed ({e!r}); using the oracle on cuda\n")
+    if mod is None:
+        from oracle import hyena_oracle as O
+        P = O.canonical(sd)
+        which = "oracle restatement (oracle/hyena_oracle.py) of the reference torch.fft path on cuda (cuFFT)"
+
+    def one():
+        if mod is not None:
+            uu = u.detach().clone().requires_grad_(True)
+            for p in mod.parameters():
+                p.grad = None
+            mod(uu).backward(dy)
+        else:
+            O.operator_fwd_bwd(u.detach(), P, dy)
+
+    try:
+        for _ in range(warmup):
+            one()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            one()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    finally:
+        mod = None
+        gc.collect()
+        torch.cuda.empty_cache()
+    return {"ms_per_step": round(ms, 3), "value": B * L / (ms * 1e-3), "unit": "nt/s", "steps": steps,
+            "warmup": warmup, "impl": which, "dtype": "f32, TF32 off"}
 
 
 # ----------------------------------------------------------------------------------------- GPU arm
@@ -390,20 +468,28 @@ def main():
         tf32_ms = b0.elapsed_time(b1) / args.steps
         torch.backends.cuda.matmul.allow_tf32 = False
 
+    # ---------------- the reference's own GPU path on the same device (rank 0, N = 1 only)
+    gpu_ref = None
+    if rank == 0 and world == 1 and not args.no_gpu_reference:
+        try:
+            gpu_ref = gpu_reference_run(op, u.detach(), dy)
+            gpu_ref["speedup"] = round(value / gpu_ref["value"], 3)
+        except Exception as e:       # out of memory on a smaller device etc.: report, do not fail the bench line
+            gpu_ref = {"unavailable": repr(e)[:200]}
+
     # ---------------- CPU baseline (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu, _ = cpu_reference_run(min(args.cpu_sample_len, L), D, 1, 1, 1, args.cpu_threads)
+        cpu, _, _ = cpu_reference_run(min(args.cpu_sample_len, L), D, 1, 1, 1, args.cpu_threads)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "nt/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"large-1m: HyenaOperator fwd+bwd, L={L} d_model={D} order=2 filter_order=64 "
-                                       f"emb_dim={EMB}, batch {B}/GPU (global {world * B}), fp32, TF32 off",
-                           "parallelism": f"dp{world} (batch-sharded replicas, grad all-reduce)",
-                           "l2": "inputs larger than L2 (u, p, dy are 1-3 GB each; 126 MB L2), no explicit flush"},
+                "config": workload_config(L, D, B, world),
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_reference": gpu_ref,
+                "speedup_vs_gpu_reference": (gpu_ref or {}).get("speedup"),
                 "tf32_projections_ms_per_step": tf32_ms,
                 "impl": "b200"}
         print(json.dumps(line), flush=True)

@@ -10,15 +10,27 @@
 namespace hy {
 
 // ---------------------------------------------------------------- complex helpers
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// A complex value is one 64-bit register pair and every helper below is written on the sm_100 packed fp32
+// instructions (add/mul/fma.rn.f32x2 -> SASS FADD2 / FMUL2 / FFMA2): a complex add is ONE instruction and a
+// complex multiply TWO.  Lane swaps and sign flips of an operand ((y, x), (-x, y), ...) are operand modifiers of
+// the packed instructions (.F32x2.LO_HI, .NP), so multiplications by +-i and conjugates stay free.
+// Rounding is identical to the scalar forms fmaf(a.x, b.x, -(a.y * b.y)) etc.
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+  return __ffma2_rn(make_float2(a.x, a.x), b, __fmul2_rn(make_float2(a.y, a.y), make_float2(-b.y, b.x)));
 }
 // a * conj(b)
 __device__ __forceinline__ float2 cmulc(float2 a, float2 b) {
-  return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+  return __ffma2_rn(make_float2(b.x, b.x), a, __fmul2_rn(make_float2(b.y, b.y), make_float2(a.y, -a.x)));
 }
+// a * s (real scale)
+__device__ __forceinline__ float2 cscale(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+// a * s + b, s real
+__device__ __forceinline__ float2 caxpy(float2 a, float s, float2 b) { return __ffma2_rn(a, make_float2(s, s), b); }
+// elementwise (not complex) product / fma of two sample pairs
+__device__ __forceinline__ float2 pmul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 pfma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 // -i * a
 __device__ __forceinline__ float2 cmul_negi(float2 a) { return make_float2(a.y, -a.x); }

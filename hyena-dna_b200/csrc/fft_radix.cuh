@@ -30,8 +30,8 @@ __device__ __forceinline__ float2 mul_w32(float2 a) {
   else if constexpr (j == 24) return INV ? cmul_negi(a) : cmul_i(a);
   else {
     constexpr float c = cos32(j);
-    constexpr float s = INV ? -sin32(j) : sin32(j);      // multiply by (c - i s)
-    return make_float2(fmaf(a.x, c, a.y * s), fmaf(a.y, c, -a.x * s));
+    constexpr float s = INV ? -sin32(j) : sin32(j);      // multiply by (c - i s): one FMUL2 + one FFMA2
+    return __ffma2_rn(a, make_float2(c, c), __fmul2_rn(make_float2(a.y, a.x), make_float2(s, -s)));
   }
 }
 

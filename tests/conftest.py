@@ -17,3 +17,12 @@ def pytest_sessionstart(session):
     # than 8-16 threads do (bench.py cpu_baseline note); keep the CPU side of the tests predictable
     import torch
     torch.set_num_threads(min(16, os.cpu_count() or 1))
+
+
+def pytest_terminal_summary(terminalreporter, exitstatus, config):
+    # how much of the parity rests on the S8(c) escape hatch (tests/parity_util.py)
+    try:
+        from tests import parity_util
+        parity_util.report(terminalreporter.write_line)
+    except Exception:
+        pass
