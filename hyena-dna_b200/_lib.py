@@ -9,7 +9,8 @@ import subprocess
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhyena_b200.so")
+# HYENA_B200_LIB: alternative build of the same library (A/B runs of kernel variants); default = the in-tree build
+LIB_PATH = os.environ.get("HYENA_B200_LIB") or os.path.join(_HERE, "libhyena_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 _lib = None
@@ -27,6 +28,9 @@ SIGNATURES = {
     "hyena_b200_profile_begin": (_i, []),
     "hyena_b200_profile_end": (_i, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_ulonglong), _i]),
     "hyena_b200_kind_name": (ctypes.c_char_p, [_i]),
+    "hyena_b200_kind_count": (_i, []),
+    "hyena_b200_spectrum_from_rfft": (_i, [c_fp, _i, c_fp, c_fp, _i, _i, _vp, _sz, _vp]),
+    "hyena_b200_spectrum_to_rfft": (_i, [c_fp, _i, c_fp, c_fp, _i, _i, _vp, _sz, _vp]),
     "hyena_b200_spectrum_elems": (_sz, [_i]),
     "hyena_b200_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "hyena_b200_workspace_min_bytes": (_sz, [_i, _i, _i, _i]),
@@ -97,7 +101,7 @@ def profile_begin():
 
 def profile_end():
     """-> {kernel class: (device ms, launches)} for the window opened by profile_begin()."""
-    n = 21
+    n = int(lib().hyena_b200_kind_count())
     ms = (ctypes.c_double * n)()
     cnt = (ctypes.c_ulonglong * n)()
     check(lib().hyena_b200_profile_end(ms, cnt, n))

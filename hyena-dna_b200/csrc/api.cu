@@ -99,16 +99,9 @@ static int log_m_for(int L) {         // M = 2^logM >= max(L, 1024)
   while (((size_t)1 << lg) < (size_t)L) ++lg;
   return lg;
 }
-// Row length.  Both 1024- and 4096-point row kernels exist; measured on B200 at L = 2^20
-// (profiles/r1_config_sweep.txt) the 1024-point rows win overall (the 4096-point backward row pass holds
-// two spectra per thread group and spills), so 1024 is the default; HYENA_B200_LOGM2=12 selects 4096-point
-// rows for M >= 2^17.
-static int pick_log_m2(int logM) {
-  static int forced = -1;
-  if (forced < 0) { const char* e = getenv("HYENA_B200_LOGM2"); forced = e ? atoi(e) : 0; }
-  if (forced == 12) return log_m2_for(logM);
-  return 10;
-}
+// Row length: 1024 points, one warp per row.  (A 4096-point variant existed in round 1 and lost: 43.85 vs 39.10 ms per
+// step at L = 2^20, profiles/r1_config_sweep.txt; removed.)
+static int pick_log_m2(int) { return 10; }
 static size_t row_bytes(int L) { return ((size_t)1 << log_m_for(L)) * sizeof(float2); }
 
 static size_t group_budget_bytes() {
@@ -247,9 +240,12 @@ HY_API const char* hyena_b200_kind_name(int kind) {
       "col_fwd<filter>", "col_fwd<gate>", "col_fwd<dc>", "col_fwd<plain>",
       "col_inv<conv_fwd>", "col_inv<bwd_dg>", "col_inv<dk>", "col_inv<plain_fwd>", "col_inv<plain_bwd>",
       "row_pass<filter>", "row_pass<conv_fwd>", "row_pass<conv_bwd>",
-      "filter_fwd", "filter_bwd", "short_conv_bwd", "twiddle_init", "filter_tc_prep", "filter_tc_fwd", "filter_tc_bwd", "filter_tc_red", "fused_conv_fwd"};
+      "filter_fwd", "filter_bwd", "short_conv_bwd", "twiddle_init", "filter_tc_prep", "filter_tc_fwd", "filter_tc_bwd", "filter_tc_red", "fused_conv_fwd",
+      "spectrum_convert"};
   return (kind >= 0 && kind < K_COUNT) ? names[kind] : "?";
 }
+
+HY_API int hyena_b200_kind_count(void) { return K_COUNT; }
 
 HY_API size_t hyena_b200_spectrum_elems(int L) { return L < 1 ? 0 : ((size_t)1 << log_m_for(L)); }
 
@@ -279,23 +275,6 @@ static int get_wimg(int D, cudaStream_t stream, float** out) {
     if (bufs[dev]) { HY_CUDA(cudaStreamSynchronize(stream)); HY_CUDA(cudaFree(bufs[dev])); }
     HY_CUDA(cudaMalloc(&bufs[dev], need));
     sizes[dev] = need;
-  }
-  *out = bufs[dev];
-  return 0;
-}
-
-// dataflow fused conv (HYENA_B200_FUSED=2): per-device completion counters (grow-only)
-static int get_flow_counters(size_t n_ints, cudaStream_t stream, int** out) {
-  int dev = -1;
-  HY_CUDA(cudaGetDevice(&dev));
-  HY_CHECK(dev >= 0 && dev < 64, "unsupported device ordinal %d", dev);
-  std::lock_guard<std::mutex> lk(g_mu);
-  static int* bufs[64] = {nullptr};
-  static size_t sizes[64] = {0};
-  if (sizes[dev] < n_ints) {
-    if (bufs[dev]) { HY_CUDA(cudaStreamSynchronize(stream)); HY_CUDA(cudaFree(bufs[dev])); }
-    HY_CUDA(cudaMalloc(&bufs[dev], n_ints * sizeof(int)));
-    sizes[dev] = n_ints;
   }
   *out = bufs[dev];
   return 0;
@@ -396,6 +375,51 @@ HY_API int hyena_b200_filter_spectrum(const float* k, float* kspec, int D, int L
   return 0;
 }
 
+/* filter = rfft(k, fft_size) (H, fft_size/2+1) complex64, natural order, unnormalised -> packed kspec (H, M).
+ * k_scratch (H*L floats) is used only when fft_size < 2M (sequences shorter than the minimum transform). */
+HY_API int hyena_b200_spectrum_from_rfft(const float* filter, int fft_size, float* kspec, float* k_scratch, int H, int L,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  if (check_shape(1, H, L)) return 1;
+  HY_CHECK(filter && kspec && aligned8(filter) && aligned8(kspec), "null or misaligned pointer");
+  HY_CHECK(fft_size >= 16 && (fft_size & (fft_size - 1)) == 0 && L <= fft_size / 2,
+           "fft_size %d must be a power of two >= 16 with L = %d <= fft_size/2 (fftconv.cpp:114-115)", fft_size, L);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int logM = log_m_for(L);
+  const int logM2 = pick_log_m2(logM), logM1 = logM - logM2;
+  if ((size_t)fft_size == ((size_t)2 << logM)) {
+    HY_CUDA(launch_rfft_to_packed(reinterpret_cast<const float2*>(filter), reinterpret_cast<float2*>(kspec), H, logM, logM1, s));
+    return 0;
+  }
+  HY_CHECK((size_t)fft_size < ((size_t)2 << logM), "fft_size %d larger than the transform of L = %d", fft_size, L);
+  HY_CHECK(k_scratch, "k_scratch is required when fft_size < 2 * spectrum_elems(L)");
+  HY_CUDA(launch_rfft_to_time_small(reinterpret_cast<const float2*>(filter), k_scratch, H, L, fft_size, s));
+  return hyena_b200_filter_spectrum(k_scratch, kspec, H, L, workspace, workspace_bytes, stream);
+}
+
+/* dk (H, L) time domain -> dfilter (H, fft_size/2+1) complex64 with irfft(dfilter, n=fft_size, norm='forward')[:L] == dk
+ * (the convention of csrc/fftconv/fftconv.cpp:235 consumed by src/ops/fftconv.py:98).  kspec_scratch: (H, M) complex. */
+HY_API int hyena_b200_spectrum_to_rfft(const float* dk, int fft_size, float* dfilter, float* kspec_scratch, int H, int L,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  if (check_shape(1, H, L)) return 1;
+  HY_CHECK(dk && dfilter && aligned8(dfilter), "null or misaligned pointer");
+  HY_CHECK(fft_size >= 16 && (fft_size & (fft_size - 1)) == 0 && L <= fft_size / 2,
+           "fft_size %d must be a power of two >= 16 with L = %d <= fft_size/2", fft_size, L);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int logM = log_m_for(L);
+  const int logM2 = pick_log_m2(logM), logM1 = logM - logM2;
+  const float scale = 1.0f / (float)fft_size;
+  if ((size_t)fft_size == ((size_t)2 << logM)) {
+    HY_CHECK(kspec_scratch && aligned8(kspec_scratch), "kspec_scratch is required");
+    if (hyena_b200_filter_spectrum(dk, kspec_scratch, H, L, workspace, workspace_bytes, stream)) return 1;
+    HY_CUDA(launch_packed_to_rfft(reinterpret_cast<const float2*>(kspec_scratch), reinterpret_cast<float2*>(dfilter), H, logM,
+                                  logM1, scale, s));
+    return 0;
+  }
+  HY_CHECK((size_t)fft_size < ((size_t)2 << logM), "fft_size %d larger than the transform of L = %d", fft_size, L);
+  HY_CUDA(launch_time_to_rfft_small(dk, reinterpret_cast<float2*>(dfilter), H, L, fft_size, scale, s));
+  return 0;
+}
+
 HY_API int hyena_b200_core_fwd(const float* p, const float* in_bias, const float* sw, const float* sb, const float* kspec,
                         const float* fbias, float* y_pre, float* c_save, float* gspec_save, int B, int D, int L,
                         void* workspace, size_t workspace_bytes, void* stream) {
@@ -414,31 +438,6 @@ HY_API int hyena_b200_core_fwd(const float* p, const float* in_bias, const float
   a.gspec = reinterpret_cast<float2*>(gspec_save);
   a.vec = ((L & 1) == 0) && aligned8(p) && aligned8(y_pre) && (!c_save || aligned8(c_save));
   a.stage = ((L & 3) == 0) && aligned16(p) && !getenv("HYENA_B200_NO_STAGE");
-  // Experimental one-kernel forms of the three passes (csrc/fused_conv.cuh), both off by default:
-  //   HYENA_B200_FUSED=1  pass 1 -> grid.sync -> pass 2 -> grid.sync -> pass 3 per row group of HYENA_B200_FUSED_MB (64)
-  //   HYENA_B200_FUSED=2  dataflow: per-row completion counters instead of grid barriers, scratch ring of
-  //                       2*HYENA_B200_FLOW_DIST+2 rows (default DIST 2)
-  static const int fused = getenv("HYENA_B200_FUSED") ? atoi(getenv("HYENA_B200_FUSED")) : 0;
-  if (fused == 1 && a.logM2 == 10 && a.logM1 >= 5) {
-    static const long fmb = getenv("HYENA_B200_FUSED_MB") ? atol(getenv("HYENA_B200_FUSED_MB")) : 64;
-    size_t per_ch = row_bytes(L) * (size_t)B;
-    int cpg = (int)(((size_t)(fmb < 1 ? 1 : fmb) << 20) / per_ch);
-    if (cpg < 1) cpg = 1;
-    if (cpg > c.nch) cpg = c.nch;
-    HY_CUDA(launch_fused_conv_fwd(a, D, cpg, s));
-    return 0;
-  }
-  if (fused == 2 && a.logM2 == 10 && a.logM1 >= 5) {
-    static const int dist_env = getenv("HYENA_B200_FLOW_DIST") ? atoi(getenv("HYENA_B200_FLOW_DIST")) : 2;
-    const int dist = dist_env < 1 ? 1 : (dist_env > 8 ? 8 : dist_env);
-    // the ring is indexed by slot * B + batch: it needs (2*dist+2) * B scratch rows; c.A holds c.nch * B
-    if (2 * dist + 2 <= c.nch) {
-      int* counters = nullptr;
-      if (get_flow_counters(3 * (size_t)B * D + 1, s, &counters)) return 1;
-      HY_CUDA(launch_flow_conv_fwd(a, B * D, dist, counters, s));
-      return 0;
-    }
-  }
   for (int c0 = 0; c0 < D; c0 += c.nch) {
     const int n = (D - c0 < c.nch) ? D - c0 : c.nch;
     a.c0 = c0;

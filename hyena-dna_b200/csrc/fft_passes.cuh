@@ -200,9 +200,9 @@ struct ColGeo {
   static constexpr int WP = 2 * C + 4, XP = 2 * C;               // staged row pitches (floats): with / without halo
   // inverse epilogue: double-buffered batches of SB slots (SB*R2 consecutive rows): 4 slots for the forward
   // epilogue (three windowed tensors), 2 for the backward one (three windowed + two plain tensors)
-  static constexpr int SB_FWD = 4, SB_BWD = 4;
+  static constexpr int SB_FWD = 8, SB_BWD = 4;
   static constexpr size_t STAGE_FWD = TWO ? (size_t)DATA_ROWS * (WP + WP) * sizeof(float) : 0;
-  static constexpr size_t BATCH_FWD_FLOATS = (size_t)SB_FWD * R2 * (3 * WP);
+  static constexpr size_t BATCH_FWD_FLOATS = (size_t)SB_FWD * R2 * WP;       // x0 windows only
   static constexpr size_t BATCH_BWD_FLOATS = (size_t)SB_BWD * R2 * (3 * WP + 2 * XP);
   // the forward epilogue is double buffered, the (larger) backward batches are not (measured: 8 half-size
   // double-buffered batches were 2x slower than 4 full-size single-buffered ones)
@@ -366,7 +366,6 @@ col_fwd_kernel(const PassArgs a) {
 // ------------------------------------------------------------------------------------------------
 struct InvCtx {
   Taps k0, k1, k2;     // taps of x0, x1, v channels
-  float fb;            // filter bias of this channel
   float red;           // per-thread partial of the reduction this mode produces
   float rw[3][3];      // INV_BWD_DG: partials of d short_filter.weight for the x0 / x1 / v channels
   float rb[3];         //             and of d short_filter.bias
@@ -391,18 +390,18 @@ template <int MODE>
 __device__ __forceinline__ void inv_load(const PassArgs& a, const InvCtx& cx, int b, int c, int t0, bool vec, InvIn& in) {
   const int L = a.L, D = a.D;
   if constexpr (MODE == INV_PLAIN_FWD) {
-    in.a = load_pair(a.src + row_off(b, c, D, L), t0, L, vec);
+    // nothing: out = y (the u * D skip term went into the filter spectrum in pass 2)
   } else if constexpr (MODE == INV_PLAIN_BWD) {
     in.a = load_pair(a.src2 + row_off(b, c, D, L), t0, L, vec);
     in.b = load_pair(a.src + row_off(b, c, D, L), t0, L, vec);
-  } else if constexpr (MODE == INV_CONV_FWD || MODE == INV_BWD_DG) {
+  } else if constexpr (MODE == INV_CONV_FWD) {
+    load_window(a.p + row_off(b, c, 3 * D, L), t0, L, vec, cx.k0.ib, in.P0);     // x0 only: c = y already holds bias * g
+  } else if constexpr (MODE == INV_BWD_DG) {
     load_window(a.p + row_off(b, c, 3 * D, L), t0, L, vec, cx.k0.ib, in.P0);
     load_window(a.p + row_off(b, D + c, 3 * D, L), t0, L, vec, cx.k1.ib, in.P1);
     load_window(a.p + row_off(b, 2 * D + c, 3 * D, L), t0, L, vec, cx.k2.ib, in.P2);
-    if constexpr (MODE == INV_BWD_DG) {
-      in.a = load_pair(a.src + row_off(b, c, D, L), t0, L, vec);
-      in.b = load_pair(a.src2 + row_off(b, c, D, L), t0, L, vec);
-    }
+    in.a = load_pair(a.src + row_off(b, c, D, L), t0, L, vec);
+    in.b = load_pair(a.src2 + row_off(b, c, D, L), t0, L, vec);
   }
 }
 
@@ -413,27 +412,25 @@ __device__ __forceinline__ void inv_finish(const PassArgs& a, InvCtx& cx, int b,
   const int L = a.L, D = a.D;
   if constexpr (MODE == INV_DK) {
     store_pair(a.out + (size_t)c * L, t0, L, vec, y);
-  } else if constexpr (MODE == INV_PLAIN_FWD) {       // out = y + u * D      hyena.py:82
-    store_pair(a.out + row_off(b, c, D, L), t0, L, vec, make_float2(fmaf(in.a.x, cx.fb, y.x), fmaf(in.a.y, cx.fb, y.y)));
-  } else if constexpr (MODE == INV_PLAIN_BWD) {       // du = corr + dout * D ; dD += dout * u
+  } else if constexpr (MODE == INV_PLAIN_FWD) {       // out = y (+ u * D inside the spectrum)      hyena.py:82
+    store_pair(a.out + row_off(b, c, D, L), t0, L, vec, y);
+  } else if constexpr (MODE == INV_PLAIN_BWD) {       // du = corr (+ dout * D inside the spectrum) ; dD += dout * u
     cx.red = fmaf(in.a.x, in.b.x, fmaf(in.a.y, in.b.y, cx.red));
-    store_pair(a.out + row_off(b, c, D, L), t0, L, vec, make_float2(fmaf(in.a.x, cx.fb, y.x), fmaf(in.a.y, cx.fb, y.y)));
-  } else if constexpr (MODE == INV_CONV_FWD) {        // c = y + bias*g ; y_pre = c * x0     hyena.py:82, :432
-    const float2 x0 = conv_window(in.P0, t0, L, cx.k0), x1 = conv_window(in.P1, t0, L, cx.k1),
-                 vv = conv_window(in.P2, t0, L, cx.k2);
-    float2 cc = make_float2(fmaf(x1.x * vv.x, cx.fb, y.x), fmaf(x1.y * vv.y, cx.fb, y.y));
-    if (a.out2) store_pair(a.out2 + row_off(b, c, D, L), t0, L, vec, cc);
-    store_pair(a.out + row_off(b, c, D, L), t0, L, vec, make_float2(cc.x * x0.x, cc.y * x0.y));
+    store_pair(a.out + row_off(b, c, D, L), t0, L, vec, y);
+  } else if constexpr (MODE == INV_CONV_FWD) {        // c = y (bias*g inside the spectrum) ; y_pre = c * x0   hyena.py:82, :432
+    const float2 x0 = conv_window(in.P0, t0, L, cx.k0);
+    if (a.out2) store_pair(a.out2 + row_off(b, c, D, L), t0, L, vec, y);
+    store_pair(a.out + row_off(b, c, D, L), t0, L, vec, pmul(y, x0));
   } else {                                            // INV_BWD_DG
     const float2 x0 = conv_window(in.P0, t0, L, cx.k0), x1 = conv_window(in.P1, t0, L, cx.k1),
                  vv = conv_window(in.P2, t0, L, cx.k2);
     const float2 dy = in.a, cs = in.b;
-    float2 dc = make_float2(dy.x * x0.x, dy.y * x0.y);
-    float2 dg = make_float2(fmaf(dc.x, cx.fb, y.x), fmaf(dc.y, cx.fb, y.y));     // + bias * dc
+    const float2 dc = pmul(dy, x0);
+    const float2 dg = y;                                         // corr(dc, k) + bias * dc (skip term inside the spectrum)
     cx.red = fmaf(dc.x, x1.x * vv.x, fmaf(dc.y, x1.y * vv.y, cx.red));           // dbias += dc * g
-    const float2 d0 = make_float2(dy.x * cs.x, dy.y * cs.y);     // d short(x0)
-    const float2 d1 = make_float2(dg.x * vv.x, dg.y * vv.y);     // d short(x1)
-    const float2 d2 = make_float2(dg.x * x1.x, dg.y * x1.y);     // d short(v)
+    const float2 d0 = pmul(dy, cs);                              // d short(x0)
+    const float2 d1 = pmul(dg, vv);                              // d short(x1)
+    const float2 d2 = pmul(dg, x1);                              // d short(v)
     store_pair(a.out2 + row_off(b, c, 3 * D, L), t0, L, vec, d0);
     store_pair(a.out2 + row_off(b, D + c, 3 * D, L), t0, L, vec, d1);
     store_pair(a.out2 + row_off(b, 2 * D + c, 3 * D, L), t0, L, vec, d2);
@@ -467,12 +464,11 @@ __device__ __forceinline__ void col_inv_body(const PassArgs& a, const int bx, co
 
   InvCtx cx{};
   cx.red = 0.f;
-  if constexpr (MODE == INV_CONV_FWD || MODE == INV_BWD_DG) {
-    cx.k0 = load_taps(a.sw, a.sb, a.in_bias, c);
+  if constexpr (MODE == INV_CONV_FWD || MODE == INV_BWD_DG) cx.k0 = load_taps(a.sw, a.sb, a.in_bias, c);
+  if constexpr (MODE == INV_BWD_DG) {
     cx.k1 = load_taps(a.sw, a.sb, a.in_bias, a.D + c);
     cx.k2 = load_taps(a.sw, a.sb, a.in_bias, 2 * a.D + c);
   }
-  if constexpr (MODE != INV_DK) cx.fb = __ldg(a.fbias + c);
 
   float2 v[32];
   if constexpr (CG::TWO) {
@@ -502,9 +498,9 @@ __device__ __forceinline__ void col_inv_body(const PassArgs& a, const int bx, co
         float* w2 = w1 + BROWS * CG::WP;
         const int row0 = BROWS * k;
         stage_windows<CG::C, kM2>(w0, p0, row0, BROWS, colbase, L);
-        stage_windows<CG::C, kM2>(w1, p1, row0, BROWS, colbase, L);
-        stage_windows<CG::C, kM2>(w2, p2, row0, BROWS, colbase, L);
         if constexpr (MODE == INV_BWD_DG) {
+          stage_windows<CG::C, kM2>(w1, p1, row0, BROWS, colbase, L);
+          stage_windows<CG::C, kM2>(w2, p2, row0, BROWS, colbase, L);
           float* x0 = w2 + BROWS * CG::WP;
           float* x1 = x0 + BROWS * CG::XP;
           stage_plain<CG::C, kM2>(x0, a.src + row_off(b, c, a.D, L), row0, BROWS, colbase, L);
@@ -537,9 +533,9 @@ __device__ __forceinline__ void col_inv_body(const PassArgs& a, const int bx, co
             InvIn in;
             const int rr = m1 - BROWS * k;
             staged_window<CG::C>(w0, rr, col, t0, cx.k0.ib, in.P0);
-            staged_window<CG::C>(w1, rr, col, t0, cx.k1.ib, in.P1);
-            staged_window<CG::C>(w2, rr, col, t0, cx.k2.ib, in.P2);
             if constexpr (MODE == INV_BWD_DG) {
+              staged_window<CG::C>(w1, rr, col, t0, cx.k1.ib, in.P1);
+              staged_window<CG::C>(w2, rr, col, t0, cx.k2.ib, in.P2);
               in.a = staged_pair<CG::C>(x0, rr, col);
               in.b = staged_pair<CG::C>(x1, rr, col);
             }
@@ -734,6 +730,15 @@ __device__ __forceinline__ void even_odd(float2 z, float2 pc, float2& e, float2&
   e = cadd(z, pc);
   o = cmul_negi(csub(z, pc));
 }
+// Same for the filter spectrum, with the skip term folded in: y = conv(k, g) + bias * g == conv(k + bias * delta, g), and
+// adding `bias` to k[0] adds the real constant `bias` to every bin of the packed spectrum, i.e. 2 * bias to the (doubled)
+// even part and nothing to the odd part.  The output pass then never re-reads g (hyena.py:82; fftconv_cuda.cu:470-476
+// adds u * D in its epilogue instead).  fb2 = 2 * bias.
+__device__ __forceinline__ void even_odd_filter(float2 z, float2 pc, float fb2, float2& e, float2& o) {
+  e = cadd(z, pc);
+  e.x += fb2;
+  o = cmul_negi(csub(z, pc));
+}
 
 // shared memory per CTA (complex elements): FILTER: rows*EX; CONV_FWD: rows*EX (spectrum aliased onto the
 // exchange area); CONV_BWD: rows*(EX + M2) (dc spectrum separate, g spectrum aliased onto the exchange area)
@@ -779,6 +784,9 @@ __device__ __forceinline__ void row_pass_body(const PassArgs& a, const int bx, c
   } else {
     // W_M^k for k = k1 + M1*(TPR s + q) = base * W_32^s,  base = W_M^{k1} * W_{M2}^{q}
     const float2 wbase = cmul(root20(a.T, (uint32_t)id.k1 << (20 - logM)), root20(a.T, (uint32_t)q << (20 - LOGM2)));
+    // skip-term coefficient of this row's channel (filter bias / D vector), doubled: see even_odd_filter
+    const int c_row = a.c0 + c0x + ((MODE == ROW_CONV_FWD) ? by / a.B : by);
+    const float fb2 = a.fbias ? 2.f * __ldg(a.fbias + c_row) : 0.f;
 
     if constexpr (MODE == ROW_CONV_FWD) {
       const int r = by;
@@ -799,7 +807,7 @@ __device__ __forceinline__ void row_pass_body(const PassArgs& a, const int bx, c
         const int pc = (M2 - k2 - id.nz) & (M2 - 1);
         float2 E, O, He, Ho;
         even_odd(ex[k2], cconj(exp_[pc]), E, O);
-        even_odd(__ldg(Krow + k2), cconj(__ldg(Kprow + pc)), He, Ho);
+        even_odd_filter(__ldg(Krow + k2), cconj(__ldg(Kprow + pc)), fb2, He, Ho);
         const float2 W = mul_w32<s, false>(wbase);
         float2 Ye = cadd(cmul(E, He), cmul(W, cmul(O, Ho)));
         float2 Yo = cadd(cmul(E, Ho), cmul(O, He));
@@ -823,7 +831,7 @@ __device__ __forceinline__ void row_pass_body(const PassArgs& a, const int bx, c
         const int pc = (M2 - k2 - id.nz) & (M2 - 1);
         float2 E, O, He, Ho;
         even_odd(zbuf[k2], cconj(zbufp[pc]), E, O);
-        even_odd(__ldg(Krow + k2), cconj(__ldg(Kprow + pc)), He, Ho);
+        even_odd_filter(__ldg(Krow + k2), cconj(__ldg(Kprow + pc)), fb2, He, Ho);
         const float2 WE = cmulc(E, mul_w32<s, false>(wbase));
         float2 Ye = cadd(cmulc(E, He), cmulc(O, Ho));
         float2 Yo = cadd(cmulc(WE, Ho), cmulc(O, He));
@@ -872,7 +880,7 @@ __device__ __forceinline__ void row_pass_body(const PassArgs& a, const int bx, c
           const int pc = (M2 - k2 - id.nz) & (M2 - 1);
           float2 E, O, He, Ho, Ge, Go;
           even_odd(zbuf[k2], cconj(zbufp[pc]), E, O);
-          even_odd(__ldg(Krow + k2), cconj(__ldg(Kprow + pc)), He, Ho);
+          even_odd_filter(__ldg(Krow + k2), cconj(__ldg(Kprow + pc)), fb2, He, Ho);
           even_odd(ex[k2], cconj(exp_[pc]), Ge, Go);
           const float2 W = mul_w32<s, false>(wbase);
           const float2 WE = cmulc(E, W);                                  // conj(W) * E
@@ -939,6 +947,7 @@ __device__ __forceinline__ void row_bwd1_staged_body(const PassArgs& a, const in
   };
   const float2 wbase = cmul(root20(a.T, (uint32_t)id.k1 << (20 - logM)), root20(a.T, (uint32_t)q << (20 - LOGM2)));
 
+  const float fb2 = a.fbias ? 2.f * __ldg(a.fbias + c) : 0.f;
   stage_row(Krow);                                                   // in flight under the forward FFT
   row_fft_to_smem<LOGM2>(Drow, ex, zbuf, q, a.T, rsync);             // dc spectrum -> zbuf (kept for both phases)
   cp_async_wait_group<0>();
@@ -950,7 +959,7 @@ __device__ __forceinline__ void row_bwd1_staged_body(const PassArgs& a, const in
     const int pc = (M2 - k2 - id.nz) & (M2 - 1);
     float2 E, O, He, Ho;
     even_odd(zbuf[k2], cconj(zbufp[pc]), E, O);
-    even_odd(kg[k2], cconj(kgp[pc]), He, Ho);
+    even_odd_filter(kg[k2], cconj(kgp[pc]), fb2, He, Ho);
     const float2 WE = cmulc(E, mul_w32<s, false>(wbase));
     float2 Ye = cadd(cmulc(E, He), cmulc(O, Ho));
     float2 Yo = cadd(cmulc(WE, Ho), cmulc(O, He));
@@ -1016,6 +1025,7 @@ __device__ __forceinline__ void row_fwd_staged_body(const PassArgs& a, const int
   cp_async_commit();
   const float2 wbase = cmul(root20(a.T, (uint32_t)id.k1 << (20 - logM)), root20(a.T, (uint32_t)q << (20 - LOGM2)));
 
+  const float fb2 = a.fbias ? 2.f * __ldg(a.fbias + c) : 0.f;
   row_fft_to_smem<LOGM2>(Arow, ex, ex, q, a.T, rsync);
   if (a.gspec) {                                                     // keep the spectrum of g for the backward pass
     float2* G = a.gspec + ((size_t)(a.c0 + ci) * a.B + (r - ci * a.B)) * rowElems + (size_t)id.k1 * M2;
@@ -1030,7 +1040,7 @@ __device__ __forceinline__ void row_fwd_staged_body(const PassArgs& a, const int
     const int pc = (M2 - k2 - id.nz) & (M2 - 1);
     float2 E, O, He, Ho;
     even_odd(ex[k2], cconj(exp_[pc]), E, O);
-    even_odd(kg[k2], cconj(kgp[pc]), He, Ho);
+    even_odd_filter(kg[k2], cconj(kgp[pc]), fb2, He, Ho);
     const float2 W = mul_w32<s, false>(wbase);
     float2 Ye = cadd(cmul(E, He), cmul(W, cmul(O, Ho)));
     float2 Yo = cadd(cmul(E, Ho), cmul(O, He));

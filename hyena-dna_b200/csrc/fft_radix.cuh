@@ -31,7 +31,7 @@ __device__ __forceinline__ float2 mul_w32(float2 a) {
   else {
     constexpr float c = cos32(j);
     constexpr float s = INV ? -sin32(j) : sin32(j);      // multiply by (c - i s): one FMUL2 + one FFMA2
-    return __ffma2_rn(a, make_float2(c, c), __fmul2_rn(make_float2(a.y, a.x), make_float2(s, -s)));
+    return cmul_cs(a, c, s);
   }
 }
 

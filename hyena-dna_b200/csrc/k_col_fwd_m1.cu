@@ -1,0 +1,2 @@
+#define HY_MODE 1
+#include "k_col_fwd.inc"

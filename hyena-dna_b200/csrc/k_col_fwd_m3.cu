@@ -1,0 +1,2 @@
+#define HY_MODE 3
+#include "k_col_fwd.inc"

@@ -1,0 +1,2 @@
+#define HY_MODE 0
+#include "k_col_inv.inc"

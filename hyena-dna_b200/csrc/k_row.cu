@@ -85,7 +85,6 @@ static cudaError_t go(const PassArgs& a, int rows, cudaStream_t s) {
 template <int MODE>
 static cudaError_t by_len(const PassArgs& a, int rows, cudaStream_t s) {
   if (a.logM2 == 10) return go<MODE, 10>(a, rows, s);
-  if (a.logM2 == 12) return go<MODE, 12>(a, rows, s);
   return cudaErrorInvalidValue;
 }
 

@@ -17,26 +17,62 @@ def _reject(**flags):
         raise HyenaB200Error(f"fftconv options not supported by the sm_100a hot path (no fallback): {bad}")
 
 
+def _is_packed(filter, H, L):
+    return (torch.is_tensor(filter) and filter.dim() == 2 and tuple(filter.shape) == (H, ops.spectrum_elems(L)))
+
+
+def _filter_to_packed(filter, H, L, fft_size):
+    """Accept either the reference's `rfft(k, n=fft_size)` (src/ops/fftconv.py:65; (H, fft_size/2+1) complex64) or the
+    packed spectrum from ops.filter_spectrum (H, spectrum_elems(L))."""
+    if fft_size and torch.is_tensor(filter) and filter.dim() == 2 and filter.shape == (H, fft_size // 2 + 1) \
+            and filter.shape[1] != ops.spectrum_elems(L):
+        return ops.spectrum_from_rfft(filter, L, fft_size), True
+    if _is_packed(filter, H, L):
+        return filter, False
+    raise HyenaB200Error(f"fftconv: filter must be rfft(k, n=fft_size) of shape ({H}, fft_size/2+1) or the packed "
+                         f"spectrum ({H}, {ops.spectrum_elems(L)}); got {tuple(filter.shape)} with fft_size={fft_size}")
+
+
 def fftconv_fwd(u, filter, D, v, head_dim, q, dropout_mask, gelu, gelu_inp, gelu_q, fft_size,
                 force_fp16_output, output_hbl_layout, fftfp16):
-    """Signature of csrc/fftconv/fftconv.cpp:53-61.  ``filter`` is the packed spectrum returned by
-    ``filter_spectrum`` (the reference passes rfft(k, fft_size); the packed form carries the same
-    information in the kernels' own order)."""
+    """Signature and filter convention of csrc/fftconv/fftconv.cpp:53-61: ``filter = torch.fft.rfft(k, n=fft_size)``
+    (H, fft_size/2+1) complex64, exactly what src/ops/fftconv.py:65 builds -- converted to the packed spectrum by
+    hyena_b200_spectrum_from_rfft.  The packed spectrum from ``ops.filter_spectrum`` is accepted as well.
+    fp32 / fp16 / bf16 ``u`` with fp32 math like the reference's dispatch (fftconv.cpp:12-31); L <= 2^20, any parity."""
     _reject(v=v is not None, q=q is not None, head_dim=head_dim != 1, dropout_mask=dropout_mask is not None,
-            gelu=gelu, gelu_inp=gelu_inp, gelu_q=gelu_q, force_fp16_output=force_fp16_output,
-            output_hbl_layout=output_hbl_layout, fftfp16=fftfp16)
-    if u.stride(-1) != 1 or not u.is_contiguous():
-        u = u.contiguous()
-    return ops.fftconv_forward(u, filter, D.contiguous())
+            gelu=gelu, gelu_inp=gelu_inp, gelu_q=gelu_q, output_hbl_layout=output_hbl_layout, fftfp16=fftfp16)
+    if u.dim() != 3:
+        raise HyenaB200Error("fftconv_fwd: u must be (B, H, L)")
+    in_dtype = u.dtype
+    if in_dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        raise HyenaB200Error(f"fftconv_fwd: unsupported input dtype {in_dtype}")
+    H, L = u.shape[1], u.shape[2]
+    kspec, _ = _filter_to_packed(filter, H, L, fft_size)
+    out = ops.fftconv_forward(u.to(torch.float32).contiguous(), kspec, D.reshape(-1).to(torch.float32).contiguous())
+    out_dtype = torch.float16 if (force_fp16_output and in_dtype != torch.bfloat16) else in_dtype    # fftconv.cpp:107-110
+    return out.to(out_dtype)
 
 
 def fftconv_bwd(dout, u, filter, D, v, head_dim, q, dropout_mask, gelu, gelu_inp, gelu_q, fft_size,
                 output_hbl_layout, fftfp16):
-    """Signature of csrc/fftconv/fftconv.cpp:134-143; returns (du, dk, dD, dv, dq) with dk already in the
-    time domain (the reference returns dk_f and inverts it in Python, src/ops/fftconv.py:98)."""
+    """Signature of csrc/fftconv/fftconv.cpp:134-143; returns (du, dfilter, dD, dv, dq).  With the reference's natural
+    ``filter`` the second output is ``dfilter`` (H, fft_size/2+1) complex64 such that
+    ``irfft(dfilter, n=fft_size, norm='forward')[..., :L] == dk`` (fftconv.cpp:235, src/ops/fftconv.py:98); with the
+    packed spectrum it is dk (H, L) in the time domain."""
     _reject(v=v is not None, q=q is not None, head_dim=head_dim != 1, dropout_mask=dropout_mask is not None,
             gelu=gelu, gelu_inp=gelu_inp, gelu_q=gelu_q, output_hbl_layout=output_hbl_layout, fftfp16=fftfp16)
-    du, dk, dD = ops.fftconv_backward(dout.contiguous(), u.contiguous(), filter, D.contiguous())
+    H, L = u.shape[1], u.shape[2]
+    kspec, natural = _filter_to_packed(filter, H, L, fft_size)
+    du, dk, dD = ops.fftconv_backward(dout.to(torch.float32).contiguous(), u.to(torch.float32).contiguous(), kspec,
+                                      D.reshape(-1).to(torch.float32).contiguous())
+    du = du.to(u.dtype)
+    if natural:
+        return du, ops.spectrum_to_rfft(dk, fft_size), dD, None, None
+    return du, dk, dD, None, None
+
+
+def _fftconv_bwd_packed(dout, u, kspec, D):
+    du, dk, dD = ops.fftconv_backward(dout.contiguous(), u.contiguous(), kspec, D.contiguous())
     return du, dk, dD, None, None
 
 
@@ -49,17 +85,37 @@ class FFTConvFunc(torch.autograd.Function):
         _reject(k_rev=k_rev is not None)
         if u.dtype != torch.float32 or k.dtype != torch.float32:
             raise HyenaB200Error("fftconv_func: fp32 inputs only")
+        if u.dim() != 3:
+            raise HyenaB200Error("fftconv_func: u must be (B, H, L)")
         u = u.contiguous()
-        D = D.to(torch.float32).contiguous()
+        H, L = u.shape[1], u.shape[2]
+        if k.dim() != 2 or k.shape[0] != H:
+            raise HyenaB200Error(f"fftconv_func: k must be (H, Lk) with H = {H}; got {tuple(k.shape)}")
+        if D.numel() != H:
+            raise HyenaB200Error(f"fftconv_func: D must have H = {H} elements; got {tuple(D.shape)}")
+        # rfft(k, n=fft_size) (src/ops/fftconv.py:65) zero-pads a short k and truncates a long one; only k[:, :L]
+        # can reach the first L outputs of the causal convolution
+        ctx.k_len = k.shape[1]
+        if k.shape[1] > L:
+            k = k[:, :L]
+        elif k.shape[1] < L:
+            k = torch.nn.functional.pad(k, (0, L - k.shape[1]))
+        D = D.reshape(H).to(torch.float32).contiguous()
         k_f = ops.filter_spectrum(k.contiguous())
         ctx.save_for_backward(u, k_f, D)
-        return fftconv_fwd(u, k_f, D, v, head_dim, q, dropout_mask, gelu, False, False, 0, force_fp16_output,
-                           output_hbl_layout, fftfp16)
+        _reject(v=v is not None, q=q is not None, head_dim=head_dim != 1, dropout_mask=dropout_mask is not None,
+                gelu=gelu, force_fp16_output=force_fp16_output, output_hbl_layout=output_hbl_layout, fftfp16=fftfp16)
+        return ops.fftconv_forward(u, k_f, D)
 
     @staticmethod
     def backward(ctx, dout):
         u, k_f, D = ctx.saved_tensors
-        du, dk, dD, _, _ = fftconv_bwd(dout, u, k_f, D, None, 1, None, None, False, False, False, 0, False, False)
+        du, dk, dD, _, _ = _fftconv_bwd_packed(dout, u, k_f, D)
+        L = u.shape[2]
+        if ctx.k_len > L:
+            dk = torch.nn.functional.pad(dk, (0, ctx.k_len - L))
+        elif ctx.k_len < L:
+            dk = dk[:, :ctx.k_len].contiguous()
         return du, dk, dD, None, None, None, None, None, None, None, None, None
 
 

@@ -29,9 +29,11 @@ def _need_cuda(*ts):
 
 
 def workspace(B, D, L, backward, device):
-    """Cached scratch buffer for the FFT passes (one per device / shape class)."""
+    """Cached scratch buffer for the FFT passes, one per (device, stream): two operators driven from different streams
+    (DDP bucket hooks, checkpoint recompute on a side stream) never share scratch, so the op stays re-entrant across
+    streams as the reference extension is (csrc/fftconv/fftconv.cpp allocates per call)."""
     n = int(_lib.lib().hyena_b200_workspace_bytes(B, D, L, int(backward)))
-    key = (device.index if device.index is not None else torch.cuda.current_device())
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream())
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < n:
         buf = torch.empty(n, dtype=torch.uint8, device=device)
@@ -50,6 +52,10 @@ def _filter_args(z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, shift, modulate
     E = z.shape[-1]
     N = W1.shape[0]
     D = W3.shape[0]
+    rows = z.shape[-2]
+    if L < 1 or L > rows or L > t.shape[-2 if t.dim() == 3 else 0]:
+        raise _lib.HyenaB200Error(f"filter length {L} exceeds the positional embedding ({rows} rows); the reference "
+                                  "returns a seq_len-long filter, callers clamp with min(L, l_max)")
     zz = z[0, :L] if z.dim() == 3 else z[:L]
     tt = (t[0, :L, 0] if t.dim() == 3 else t[:L]).contiguous()
     if zz.stride(-1) != 1:
@@ -162,6 +168,53 @@ def filter_spectrum(k):
     return spec
 
 
+def _check_spectrum(kspec, H, L, what):
+    """The packed spectrum is opaque but its type and shape are not: (H, spectrum_elems(L)) complex64, contiguous, on the
+    same device -- anything else (e.g. the reference's rfft(k, fft_size), src/ops/fftconv.py:65) would be read out of
+    bounds or silently misinterpreted by the kernels."""
+    M = spectrum_elems(L)
+    if not (torch.is_tensor(kspec) and kspec.is_cuda and kspec.dtype == torch.complex64 and kspec.dim() == 2
+            and tuple(kspec.shape) == (H, M) and kspec.is_contiguous()):
+        got = (tuple(kspec.shape), kspec.dtype) if torch.is_tensor(kspec) else type(kspec)
+        raise _lib.HyenaB200Error(f"{what}: filter spectrum must be the packed form from filter_spectrum(): contiguous "
+                                  f"complex64 ({H}, {M}) on the GPU; got {got}.  For the reference's rfft(k, fft_size) "
+                                  "use fftconv.fftconv_fwd / fftconv_bwd, which convert it")
+
+
+def spectrum_from_rfft(filt, L, fft_size):
+    """rfft(k, n=fft_size) (H, fft_size/2+1) complex64 -- the filter the reference extension takes
+    (src/ops/fftconv.py:64-65) -- to the packed spectrum the kernels consume."""
+    if not (torch.is_tensor(filt) and filt.is_cuda and filt.dtype == torch.complex64 and filt.dim() == 2
+            and filt.shape[1] == fft_size // 2 + 1):
+        raise _lib.HyenaB200Error(f"filter must be a CUDA complex64 (H, fft_size/2+1 = {fft_size // 2 + 1}) tensor")
+    filt = filt.contiguous()
+    H = filt.shape[0]
+    M = spectrum_elems(L)
+    spec = torch.empty(H, M, dtype=torch.complex64, device=filt.device)
+    ksc = torch.empty(H, L, dtype=torch.float32, device=filt.device) if fft_size < 2 * M else None
+    ws = workspace(1, H, L, False, filt.device)
+    with torch.cuda.device(filt.device):
+        _lib.check(_lib.lib().hyena_b200_spectrum_from_rfft(_ptr(filt), int(fft_size), _ptr(spec), _ptr(ksc), H, int(L),
+                                                            _ptr(ws), ws.numel(), _stream()))
+    return spec
+
+
+def spectrum_to_rfft(dk, fft_size):
+    """dk (H, L) time domain -> dfilter (H, fft_size/2+1) complex64 with irfft(dfilter, n=fft_size, norm='forward')[:L]
+    == dk: what csrc/fftconv/fftconv.cpp:235 returns and src/ops/fftconv.py:98 consumes."""
+    _need_cuda(dk)
+    dk = dk.contiguous()
+    H, L = dk.shape
+    M = spectrum_elems(L)
+    out = torch.empty(H, fft_size // 2 + 1, dtype=torch.complex64, device=dk.device)
+    ssc = torch.empty(H, M, dtype=torch.complex64, device=dk.device) if fft_size == 2 * M else None
+    ws = workspace(1, H, L, False, dk.device)
+    with torch.cuda.device(dk.device):
+        _lib.check(_lib.lib().hyena_b200_spectrum_to_rfft(_ptr(dk), int(fft_size), _ptr(out), _ptr(ssc), H, int(L),
+                                                          _ptr(ws), ws.numel(), _stream()))
+    return out
+
+
 def _save_spectrum():
     import os
     return os.environ.get("HYENA_B200_SAVE_SPECTRUM", "1") != "0"
@@ -171,7 +224,11 @@ def core_forward(p, in_bias, sw, sb, kspec, fbias, save_c):
     _need_cuda(p, in_bias, sw, sb, fbias)
     B, C3, L = p.shape
     D = C3 // 3
-    assert p.is_contiguous() and kspec.is_contiguous()
+    if C3 != 3 * D or not p.is_contiguous():
+        raise _lib.HyenaB200Error("core_forward: p must be contiguous (B, 3D, L)")
+    _check_spectrum(kspec, D, L, "core_forward")
+    if sw.numel() != 3 * C3 or sb.numel() != C3 or fbias.numel() != D or (in_bias is not None and in_bias.numel() != C3):
+        raise _lib.HyenaB200Error("core_forward: short filter / bias shapes do not match p")
     y = torch.empty(B, D, L, dtype=torch.float32, device=p.device)
     c = torch.empty(B, D, L, dtype=torch.float32, device=p.device) if save_c else None
     # spectrum of the gated input, rows ordered (c, b): saves a column pass + a row FFT per row in backward
@@ -190,6 +247,9 @@ def core_backward(dy_pre, p, in_bias, sw, sb, kspec, fbias, c_saved, gspec=None)
     B, C3, L = p.shape
     D = C3 // 3
     dev = p.device
+    _check_spectrum(kspec, D, L, "core_backward")
+    if tuple(dy_pre.shape) != (B, D, L) or tuple(c_saved.shape) != (B, D, L):
+        raise _lib.HyenaB200Error("core_backward: dy_pre / c_saved must be (B, D, L)")
     dy_pre = dy_pre.contiguous()
     dp = torch.empty_like(p)
     ds = torch.empty_like(p)
@@ -234,7 +294,12 @@ class HyenaCoreFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------ plain fftconv
 def fftconv_forward(u, kspec, Dvec):
     _need_cuda(u, Dvec)
+    if u.dim() != 3 or not u.is_contiguous():
+        raise _lib.HyenaB200Error("fftconv_forward: u must be contiguous (B, H, L)")
     B, H, L = u.shape
+    _check_spectrum(kspec, H, L, "fftconv_forward")
+    if Dvec.numel() != H or not Dvec.is_contiguous():
+        raise _lib.HyenaB200Error(f"fftconv_forward: D must have {H} contiguous elements, got {tuple(Dvec.shape)}")
     out = torch.empty_like(u)
     ws = workspace(B, H, L, False, u.device)
     with torch.cuda.device(u.device):
@@ -245,7 +310,12 @@ def fftconv_forward(u, kspec, Dvec):
 
 def fftconv_backward(dout, u, kspec, Dvec):
     _need_cuda(dout, u, Dvec)
+    if u.dim() != 3 or not u.is_contiguous() or tuple(dout.shape) != tuple(u.shape) or not dout.is_contiguous():
+        raise _lib.HyenaB200Error("fftconv_backward: u and dout must be contiguous (B, H, L) of the same shape")
     B, H, L = u.shape
+    _check_spectrum(kspec, H, L, "fftconv_backward")
+    if Dvec.numel() != H or not Dvec.is_contiguous():
+        raise _lib.HyenaB200Error(f"fftconv_backward: D must have {H} contiguous elements, got {tuple(Dvec.shape)}")
     du = torch.empty_like(u)
     dk = torch.empty(H, L, dtype=torch.float32, device=u.device)
     dD = torch.zeros(H, dtype=torch.float32, device=u.device)

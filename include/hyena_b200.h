@@ -50,10 +50,11 @@ HY_API int hyena_b200_max_seqlen(void);
 
 /* Optional per-launch timing with CUDA events on the launching stream (used by bench.py's roofline leg).
  * profile_begin() starts a window; profile_end() synchronises the device and returns, per kernel class
- * (index < 16, name from hyena_b200_kind_name), the summed device milliseconds and the launch count. */
+ * (index < hyena_b200_kind_count(), name from hyena_b200_kind_name), the summed device milliseconds and the launch count. */
 HY_API int hyena_b200_profile_begin(void);
 HY_API int hyena_b200_profile_end(double* ms_by_kind, unsigned long long* launches_by_kind, int n);
 HY_API const char* hyena_b200_kind_name(int kind);
+HY_API int hyena_b200_kind_count(void);
 
 /* M: complex elements per channel of a filter spectrum for sequence length L (power of two >= L, >= 1024) */
 HY_API size_t hyena_b200_spectrum_elems(int L);
@@ -139,6 +140,19 @@ HY_API int hyena_b200_fftconv_fwd(const float* u, const float* kspec, const floa
 HY_API int hyena_b200_fftconv_bwd(const float* dout, const float* u, const float* kspec, const float* Dvec,
                            float* du, float* dk, float* dD, int B, int H, int L,
                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- the reference extension's filter convention ---------------------------------------------
+ * csrc/fftconv/fftconv.cpp:53-61 takes `filter = torch.fft.rfft(k, n=fft_size)`: (H, fft_size/2+1) complex64, natural
+ * bin order, unnormalised (src/ops/fftconv.py:64-65); fftconv.cpp:134-143,235 returns `dfilter` in the same layout with
+ * irfft(dfilter, n=fft_size, norm='forward')[:L] == dk (src/ops/fftconv.py:94-98).  These two entry points convert
+ * between that convention and the packed kspec / the time-domain dk of fftconv_fwd / fftconv_bwd above, so that an
+ * unmodified src/ops/fftconv.py:FFTConvFunc binds to this library.  fft_size: power of two >= 16 with
+ * L <= fft_size/2 (fftconv.cpp:114-115).  k_scratch (H*L floats) is needed only when fft_size < 2*spectrum_elems(L);
+ * kspec_scratch (H * spectrum_elems(L) complex64) only when fft_size == 2*spectrum_elems(L). */
+HY_API int hyena_b200_spectrum_from_rfft(const float* filter, int fft_size, float* kspec, float* k_scratch, int H, int L,
+                                  void* workspace, size_t workspace_bytes, void* stream);
+HY_API int hyena_b200_spectrum_to_rfft(const float* dk, int fft_size, float* dfilter, float* kspec_scratch, int H, int L,
+                                void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- projections (library GEMM at the boundary of the custom-kernel span) ------------------------
  * in_proj / out_proj (hyena.py:350-351, :391, :440) are plain GEMMs and stay cuBLASLt calls.  These two

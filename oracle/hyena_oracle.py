@@ -192,3 +192,20 @@ def nucleotide_activations(B, L, D, seed=2222):
     ids = torch.randint(7, 11, (B, L), generator=g)
     table = torch.randn(16, D, generator=g) * 0.02
     return F.layer_norm(table[ids], (D,)), ids
+
+
+# ----------------------------------------------------------------------------- the reference's FFTConvFunc protocol
+def reference_fftconv_protocol(fftconv_fwd, fftconv_bwd, u, k, D, dout):
+    """Drive an extension exposing ``fftconv_fwd`` / ``fftconv_bwd`` exactly the way the reference's autograd wrapper
+    does (src/ops/fftconv.py:61-103, gelu=False, no dropout / v / q / k_rev): fft_size from the sequence length (:64),
+    ``k_f = rfft(k, n=fft_size)`` built with torch (:65), ``dk = irfft(dk_f, n=fft_size, norm='forward')[..., :L]``
+    (:98).  Returns out, du, dk, dD.  Test infrastructure: lets the extension-level ABI be checked without importing
+    /root/reference on the GPU box."""
+    seqlen = u.shape[-1]
+    fft_size = max(2 * 2 ** int(math.ceil(math.log2(seqlen))), 16)
+    k_f = torch.fft.rfft(k, n=fft_size).contiguous()
+    out = fftconv_fwd(u, k_f, D.contiguous(), None, 1, None, None, False, False, False, fft_size, False, False, False)
+    du, dk_f, dD, _, _ = fftconv_bwd(dout.contiguous(), u, k_f, D.contiguous(), None, 1, None, None, False, False, False,
+                                     fft_size, False, False)
+    dk = torch.fft.irfft(dk_f, n=fft_size, norm='forward')[..., :seqlen]
+    return out, du, dk, dD

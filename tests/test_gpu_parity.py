@@ -393,3 +393,68 @@ def test_wide_model_filter_paths():
     for name in names:
         short = name[len("filter_fn."):]
         _close(got[short].grad, Q[name].grad, f"wide grad {short}", rtol=2e-3, atol=2e-5)
+
+
+# ------------------------------------------------------------------------------------------ extension-level ABI
+@pytest.mark.parametrize("L", [64, 250, 512, 1024, 4096, 8192, 65536])
+def test_extension_abi_takes_reference_filter_convention(L):
+    """fftconv_fwd / fftconv_bwd driven exactly as src/ops/fftconv.py:61-103 drives the reference extension:
+    filter = rfft(k, n=fft_size) in, dfilter (H, fft_size/2+1) complex64 out (csrc/fftconv/fftconv.cpp:53-61,134-143,235)."""
+    import hyena_dna_b200 as H
+    from importlib import import_module
+    F = import_module("hyena_dna_b200.fftconv")
+    dev = _dev()
+    B, Hc = 2, 3
+    g = torch.Generator().manual_seed(100 + L)
+    u = torch.randn(B, Hc, L, generator=g)
+    k = torch.randn(Hc, L, generator=g) * torch.exp(-torch.arange(L) / (0.05 * L + 1))[None] / math.sqrt(0.05 * L + 1)
+    Dv = torch.randn(Hc, generator=g)
+    dout = torch.randn(B, Hc, L, generator=g)
+    ur, kr, Dr = (x.double().clone().requires_grad_(True) for x in (u, k, Dv))
+    ref = O.fftconv_ref(ur, kr, Dr)
+    ref.backward(dout.double())
+    out, du, dk, dD = O.reference_fftconv_protocol(F.fftconv_fwd, F.fftconv_bwd, u.to(dev), k.to(dev), Dv.to(dev),
+                                                   dout.to(dev))
+    fft_size = max(2 * 2 ** int(math.ceil(math.log2(L))), 16)
+    _close(out, ref, f"ext out L={L}")
+    _close(du, ur.grad, f"ext du L={L}")
+    _close(dk, kr.grad, f"ext dk L={L}")
+    _close(dD, Dr.grad, f"ext dD L={L}", rtol=2e-3)
+    # dtype dispatch of the reference extension (fftconv.cpp:12-31): half / bfloat16 I/O with fp32 math
+    for dt, tol in ((torch.float16, 2e-3), (torch.bfloat16, 1.6e-2)):
+        k_f = torch.fft.rfft(k.to(dev), n=fft_size).contiguous()
+        o16 = F.fftconv_fwd(u.to(dev).to(dt), k_f, Dv.to(dev), None, 1, None, None, False, False, False, fft_size, False,
+                            False, False)
+        assert o16.dtype == dt
+        ref16 = O.fftconv_ref(u.to(dt).double(), k.double(), Dv.double())
+        _close(o16.float(), ref16, f"ext out {dt} L={L}", rtol=tol, atol=tol)
+
+
+def test_validation_of_spectrum_and_filter_shapes():
+    """mismatched k / kspec / D used to give silently wrong results."""
+    import hyena_dna_b200 as H
+    dev = _dev()
+    u = torch.randn(1, 2, 3000, device=dev)
+    D = torch.randn(2, device=dev)
+    good = H.ops.filter_spectrum(torch.randn(2, 3000, device=dev))
+    H.ops.fftconv_forward(u, good, D)
+    with pytest.raises(H.HyenaB200Error):          # the reference's rfft(k, fft_size) handed to the packed-spectrum op
+        H.ops.fftconv_forward(u, torch.fft.rfft(torch.randn(2, 3000, device=dev), n=8192), D)
+    with pytest.raises(H.HyenaB200Error):          # spectrum of another length class
+        H.ops.fftconv_forward(u, H.ops.filter_spectrum(torch.randn(2, 1000, device=dev)), D)
+    with pytest.raises(H.HyenaB200Error):          # wrong number of rows
+        H.ops.fftconv_forward(u, H.ops.filter_spectrum(torch.randn(3, 3000, device=dev)), D)
+    with pytest.raises(H.HyenaB200Error):
+        H.ops.fftconv_forward(u, good, torch.randn(3, device=dev))
+    with pytest.raises(H.HyenaB200Error):
+        H.fftconv_func(u, torch.randn(3, 3000, device=dev), D, gelu=False)
+    # a shorter / longer k is zero-padded / truncated like rfft(k, n=fft_size) does
+    k_short = torch.randn(2, 1000, device=dev)
+    a = H.fftconv_func(u, k_short, D, gelu=False)
+    b = H.fftconv_func(u, torch.nn.functional.pad(k_short, (0, 2000)), D, gelu=False)
+    assert torch.equal(a, b)
+    k_long = torch.randn(2, 5000, device=dev)
+    assert torch.equal(H.fftconv_func(u, k_long, D, gelu=False), H.fftconv_func(u, k_long[:, :3000].contiguous(), D, gelu=False))
+    f = H.HyenaFilter(8, emb_dim=5, order=64, seq_len=128, w=10.0).to(dev)
+    with pytest.raises(H.HyenaB200Error):          # filter longer than the positional embedding
+        f.filter(129)
