@@ -241,7 +241,7 @@ HY_API const char* hyena_b200_kind_name(int kind) {
       "col_inv<conv_fwd>", "col_inv<bwd_dg>", "col_inv<dk>", "col_inv<plain_fwd>", "col_inv<plain_bwd>",
       "row_pass<filter>", "row_pass<conv_fwd>", "row_pass<conv_bwd>",
       "filter_fwd", "filter_bwd", "short_conv_bwd", "twiddle_init", "filter_tc_prep", "filter_tc_fwd", "filter_tc_bwd", "filter_tc_red", "fused_conv_fwd",
-      "spectrum_convert"};
+      "spectrum_convert", "proj_prep", "proj_gemm", "proj_wgrad"};
   return (kind >= 0 && kind < K_COUNT) ? names[kind] : "?";
 }
 
@@ -453,7 +453,7 @@ HY_API int hyena_b200_core_bwd(const float* dy_pre, const float* p, const float*
                         float* dp, float* dk, float* dsw, float* dsb, float* dfbias, float* d_in_bias,
                         float* ds_scratch, int B, int D, int L, void* workspace, size_t workspace_bytes, void* stream) {
   if (check_shape(B, D, L)) return 1;
-  HY_CHECK(dy_pre && p && sw && sb && kspec && fbias && c_saved && dp && dk && dsw && dsb && dfbias && ds_scratch,
+  HY_CHECK(dy_pre && p && sw && sb && kspec && fbias && c_saved && dk && dsw && dsb && dfbias && ds_scratch,
            "null pointer");
   cudaStream_t s = (cudaStream_t)stream;
   Twiddles T;
@@ -466,7 +466,7 @@ HY_API int hyena_b200_core_bwd(const float* dy_pre, const float* p, const float*
   a.kspec = reinterpret_cast<const float2*>(kspec);
   a.p = p; a.in_bias = in_bias; a.sw = sw; a.sb = sb; a.fbias = fbias;
   a.vec = ((L & 1) == 0) && aligned8(p) && aligned8(dy_pre) && aligned8(c_saved) && aligned8(dk) &&
-          aligned8(ds_scratch) && aligned8(dp);
+          aligned8(ds_scratch);
   a.stage = ((L & 3) == 0) && aligned16(p) && aligned16(dy_pre) && aligned16(c_saved) && !getenv("HYENA_B200_NO_STAGE");
   for (int c0 = 0; c0 < D; c0 += c.nch) {
     const int n = (D - c0 < c.nch) ? D - c0 : c.nch;
@@ -488,9 +488,47 @@ HY_API int hyena_b200_core_bwd(const float* dy_pre, const float* p, const float*
     a.B = 1; a.out = dk;
     HY_CUDA(launch_col_inv(INV_DK, a, n, s));
   }
-  // pass 3 already accumulated dsw / dsb from the operand windows it had staged: no second read of p here
-  ShortBwdArgs sa{ds_scratch, nullptr, in_bias, sw, dp, dsw, dsb, d_in_bias, L, 3 * D, a.vec};
-  HY_CUDA(launch_short_bwd(sa, B, s));
+  // pass 3 already accumulated dsw / dsb from the operand windows it had staged: no second read of p here.
+  // dp == NULL: the caller consumes ds directly (hyena_b200_proj_gemm / proj_wgrad apply the transposed short filter on
+  // the fly and d in_proj.bias follows from dsb and two edge samples), so dp never exists in HBM.
+  if (dp) {
+    ShortBwdArgs sa{ds_scratch, nullptr, in_bias, sw, dp, dsw, dsb, d_in_bias, L, 3 * D, a.vec && aligned8(dp)};
+    HY_CUDA(launch_short_bwd(sa, B, s));
+  }
+  return 0;
+}
+
+/* OUT[pos][n] = sum_k ACT[pos][k] W'[n][k] (+ bias[n]) on tcgen05, fp32 accuracy (3xTF32); see include/hyena_b200.h */
+HY_API size_t hyena_b200_proj_wimg_bytes(int N, int K) { return (N < 1 || K < 1) ? 0 : proj_wimg_bytes(N, K); }
+
+HY_API int hyena_b200_proj_gemm(const float* act, int act_layout, const float* W, int ldw, int w_transposed,
+                         const float* bias, const float* fir, float* out, int out_layout, int B, int L, int K, int N,
+                         int l_begin, int l_len, void* wimg, size_t wimg_bytes, void* stream) {
+  HY_CHECK(act && W && out && wimg, "null pointer");
+  if (l_len <= 0) { l_begin = 0; l_len = L; }
+  HY_CHECK(l_begin >= 0 && l_begin + l_len <= L, "position range [%d, %d) outside [0, %d)", l_begin, l_begin + l_len, L);
+  HY_CHECK(B >= 1 && L >= 1 && K >= 1 && N >= 1, "bad shape B=%d L=%d K=%d N=%d", B, L, K, N);
+  HY_CHECK((act_layout == 0 || act_layout == 1) && (out_layout == 0 || out_layout == 1), "bad layout code");
+  HY_CHECK(!fir || act_layout == 1, "the fused transposed short filter needs a channel-major activation");
+  HY_CHECK(aligned16(act) && aligned16(out) && aligned16(wimg) && (!bias || aligned16(bias)), "pointers must be 16-byte aligned");
+  HY_CHECK(wimg_bytes >= proj_wimg_bytes(N, K), "weight image scratch too small: %zu < %zu", wimg_bytes, proj_wimg_bytes(N, K));
+  HY_CHECK(ldw >= (w_transposed ? N : K), "ldw %d too small", ldw);
+  HY_CUDA(launch_proj_gemm(act, act_layout, W, ldw, w_transposed, bias, fir, out, out_layout, B, L, K, N, l_begin, l_len,
+                           reinterpret_cast<float*>(wimg), (cudaStream_t)stream));
+  return 0;
+}
+
+HY_API size_t hyena_b200_proj_wgrad_scratch_bytes(int M, int N) { return (M < 1 || N < 1) ? 0 : proj_wgrad_scratch_bytes(M, N); }
+
+HY_API int hyena_b200_proj_wgrad(const float* X, const float* Y, const float* fir, float* dW, int transposed_out, float beta,
+                          int B, int L, int M, int N, void* scratch, size_t scratch_bytes, void* stream) {
+  HY_CHECK(X && Y && dW && scratch, "null pointer");
+  HY_CHECK(B >= 1 && L >= 1 && M >= 1 && N >= 1, "bad shape B=%d L=%d M=%d N=%d", B, L, M, N);
+  HY_CHECK(aligned16(X) && aligned16(Y) && aligned16(scratch), "pointers must be 16-byte aligned");
+  HY_CHECK(scratch_bytes >= proj_wgrad_scratch_bytes(M, N), "scratch too small: %zu < %zu", scratch_bytes,
+           proj_wgrad_scratch_bytes(M, N));
+  HY_CUDA(launch_proj_wgrad(X, Y, fir, dW, transposed_out, beta, B, L, M, N, reinterpret_cast<float*>(scratch),
+                            (cudaStream_t)stream));
   return 0;
 }
 

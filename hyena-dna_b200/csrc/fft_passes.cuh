@@ -314,17 +314,14 @@ __device__ __forceinline__ void col_fwd_body(const PassArgs& a, const int bx, co
     static_for<16, 32>([&](auto n_) { v[decltype(n_)::value] = make_float2(0.f, 0.f); });
     block_fft<CG::TWO ? LOGM1 : 5, false, true>(v, smem + col * CG::PITCH, q, a.T.tw1024, CtaSync{});
     // 4-step twiddle W_M^{m2*k1}, k1 = R2*s + q : geometric in s
-    const int sh = 20 - logM;
     const uint32_t Mmask = (1u << logM) - 1u;
     const uint32_t eb = ((uint32_t)m2 * (uint32_t)q) & Mmask;
     const uint32_t es = ((uint32_t)m2 * (uint32_t)CG::R2) & Mmask;
-    float2 base = root20(a.T, eb << sh);
-    float2 s1 = root20(a.T, (es & Mmask) << sh);
-    float2 s2 = root20(a.T, ((2u * es) & Mmask) << sh);
-    float2 s4 = root20(a.T, ((4u * es) & Mmask) << sh);
-    float2 s8 = root20(a.T, ((8u * es) & Mmask) << sh);
-    float2 s16 = root20(a.T, ((16u * es) & Mmask) << sh);
-    mul_geometric<false>(v, base, s1, s2, s4, s8, s16, SlotIdx<CG::TWO ? LOGM1 : 5>{});
+    {
+      float2 lo[8], hi[4];
+      twiddle_factors20(a.T, eb, es, logM, lo, hi);
+      mul_twiddles<false>(v, lo, hi, SlotIdx<CG::TWO ? LOGM1 : 5>{});
+    }
     static_for<0, 32>([&](auto s_) {
       constexpr int s = decltype(s_)::value;
       const int k1 = CG::R2 * s + q;
@@ -637,7 +634,7 @@ struct RowGeo {
   static constexpr int M2 = 1 << LOGM2;
   static constexpr int TPR = M2 / 32;                         // threads per row
   static constexpr int ROWS = 256 / TPR;                      // rows per full CTA (8 or 2)
-  static constexpr int EX = LOGM2 == 10 ? 32 * 33 : kEx4096;  // exchange elems per row (>= M2: also holds a spectrum)
+  static constexpr int EX = 32 * 33;                          // exchange elems per row (>= M2: also holds a spectrum)
   static_assert(EX >= M2, "the exchange area doubles as a natural-order row buffer");
 };
 
@@ -676,12 +673,12 @@ struct RowSync {
 
 template <int LOGM2, bool INV>
 __device__ __forceinline__ void row_fft(float2 (&v)[32], float2* ex, int q, const Twiddles& T, RowSync<LOGM2> sync) {
-  if constexpr (LOGM2 == 10) block_fft<10, INV, false>(v, ex, q, T.tw1024, sync);
-  else block_fft4096<INV>(v, ex, q, T, sync);
+  static_assert(LOGM2 == 10, "1024-point rows");
+  block_fft<10, INV, false>(v, ex, q, T.tw1024, sync);
 }
 template <int LOGM2>
 struct RowSlot {
-  __host__ __device__ static constexpr int at(int s) { return LOGM2 == 10 ? Geo<10>::slot(s) : Slot4096::at(s); }
+  __host__ __device__ static constexpr int at(int s) { return Geo<10>::slot(s); }
 };
 
 // forward FFT of one row; natural bin k2 = TPR*s + q left in dst[k2] (dst may be `ex` itself)
@@ -708,17 +705,14 @@ __device__ __forceinline__ void row_ifft_store(float2 (&v)[32], float2* ex, floa
                                                int logM, const Twiddles& T, RowSync<LOGM2> sync) {
   constexpr int TPR = RowGeo<LOGM2>::TPR;
   row_fft<LOGM2, true>(v, ex, q, T, sync);
-  const int sh = 20 - logM;
   const uint32_t Mmask = (1u << logM) - 1u;
   const uint32_t eb = ((uint32_t)k1 * (uint32_t)q) & Mmask;
   const uint32_t es = ((uint32_t)k1 * (uint32_t)TPR) & Mmask;
-  float2 base = root20(T, eb << sh);
-  float2 s1 = root20(T, (es & Mmask) << sh);
-  float2 s2 = root20(T, ((2u * es) & Mmask) << sh);
-  float2 s4 = root20(T, ((4u * es) & Mmask) << sh);
-  float2 s8 = root20(T, ((8u * es) & Mmask) << sh);
-  float2 s16 = root20(T, ((16u * es) & Mmask) << sh);
-  mul_geometric<true>(v, base, s1, s2, s4, s8, s16, RowSlot<LOGM2>{});
+  {
+    float2 lo[8], hi[4];
+    twiddle_factors20(T, eb, es, logM, lo, hi);
+    mul_twiddles<true>(v, lo, hi, RowSlot<LOGM2>{});
+  }
   static_for<0, 32>([&](auto s_) {
     constexpr int s = decltype(s_)::value;
     dst[TPR * s + q] = v[RowSlot<LOGM2>::at(s)];
@@ -783,7 +777,7 @@ __device__ __forceinline__ void row_pass_body(const PassArgs& a, const int bx, c
     return;
   } else {
     // W_M^k for k = k1 + M1*(TPR s + q) = base * W_32^s,  base = W_M^{k1} * W_{M2}^{q}
-    const float2 wbase = cmul(root20(a.T, (uint32_t)id.k1 << (20 - logM)), root20(a.T, (uint32_t)q << (20 - LOGM2)));
+    const float2 wbase = root20(a.T, ((uint32_t)id.k1 + ((uint32_t)q << a.logM1)) << (20 - logM));
     // skip-term coefficient of this row's channel (filter bias / D vector), doubled: see even_odd_filter
     const int c_row = a.c0 + c0x + ((MODE == ROW_CONV_FWD) ? by / a.B : by);
     const float fb2 = a.fbias ? 2.f * __ldg(a.fbias + c_row) : 0.f;
@@ -907,7 +901,7 @@ __device__ __forceinline__ void row_pass_body(const PassArgs& a, const int bx, c
 // (issued before the forward row FFT / before the first inverse FFT, so the 2 x 64 dependent __ldg's per thread of the
 // two pointwise phases -- `long_scoreboard`, the top stall of the kernel -- become shared-memory reads).  One 8 KB
 // buffer per row, reused for k then g; the partner row's buffer supplies the mirrored bins.  Shared memory per CTA:
-// rows * (EX + 2 * M2) complex = 99 KB for four rows, two CTAs per SM.  Experimental: HYENA_B200_ROW_BWD1_STAGE=1.
+// rows * (EX + 2 * M2) complex = 99 KB for four rows, two CTAs per SM.  Default for batch 1 (2.75 vs 3.51 ms at large-1m, profiles/r2_ab.txt); HYENA_B200_ROW_BWD1_STAGE=0 selects the register-load form.
 template <int LOGM2>
 __host__ __device__ constexpr size_t row_bwd1_staged_smem_elems(int rows) {
   return (size_t)rows * (RowGeo<LOGM2>::EX + 2 * RowGeo<LOGM2>::M2);
@@ -945,7 +939,7 @@ __device__ __forceinline__ void row_bwd1_staged_body(const PassArgs& a, const in
     }
     cp_async_commit();
   };
-  const float2 wbase = cmul(root20(a.T, (uint32_t)id.k1 << (20 - logM)), root20(a.T, (uint32_t)q << (20 - LOGM2)));
+  const float2 wbase = root20(a.T, ((uint32_t)id.k1 + ((uint32_t)q << a.logM1)) << (20 - logM));
 
   const float fb2 = a.fbias ? 2.f * __ldg(a.fbias + c) : 0.f;
   stage_row(Krow);                                                   // in flight under the forward FFT
@@ -984,70 +978,6 @@ __device__ __forceinline__ void row_bwd1_staged_body(const PassArgs& a, const in
   });
   float2* Krow_out = a.A3 + (size_t)ci * rowElems + (size_t)id.k1 * M2;
   row_ifft_store<LOGM2>(v, ex, Krow_out, q, id.k1, logM, a.T, rsync);
-}
-
-// ROW_CONV_FWD with the filter spectrum row staged by cp.async under the forward row FFT (same idea as
-// row_bwd1_staged_body).  Shared memory per CTA: rows * (EX + M2) complex = 66.5 KB for four rows (128 threads),
-// three CTAs per SM.  Experimental: HYENA_B200_ROW_FWD_STAGE=1.
-template <int LOGM2>
-__host__ __device__ constexpr size_t row_fwd_staged_smem_elems(int rows) {
-  return (size_t)rows * (RowGeo<LOGM2>::EX + RowGeo<LOGM2>::M2);
-}
-
-template <int LOGM2>
-__device__ __forceinline__ void row_fwd_staged_body(const PassArgs& a, const int bx, const int by, unsigned char* smem_raw) {
-  using RG = RowGeo<LOGM2>;
-  constexpr int M2 = RG::M2, TPR = RG::TPR;
-  static_assert(LOGM2 == 10, "one warp per row");
-  float2* smem = reinterpret_cast<float2*>(smem_raw);
-  const int M1 = 1 << a.logM1;
-  const int logM = a.logM1 + LOGM2;
-  const int slot = threadIdx.x / TPR, q = threadIdx.x % TPR;
-  const int nslots = blockDim.x / TPR;
-  const RowIds id = row_ids(M1, nslots, bx, slot);
-  const size_t rowElems = (size_t)M1 * M2;
-  const RowSync<LOGM2> rsync{1 + slot};
-
-  float2* ex = smem + slot * RG::EX;                                 // exchange area, then this row's spectrum
-  const float2* exp_ = smem + id.pslot * RG::EX;
-  float2* kg = smem + nslots * RG::EX + slot * M2;                   // staged filter spectrum row
-  const float2* kgp = smem + nslots * RG::EX + id.pslot * M2;
-
-  const int r = by;
-  const int ci = r / a.B, c = a.c0 + ci;
-  float2* Arow = a.A + (size_t)r * rowElems + (size_t)id.k1 * M2;
-  const float2* Krow = a.kspec + (size_t)c * rowElems + (size_t)id.k1 * M2;
-#pragma unroll
-  for (int i = 0; i < M2 / 2 / TPR; ++i) {                           // 8 KB = 512 x 16 B, coalesced
-    const int e = 2 * (TPR * i + q);
-    cp_async16(kg + e, Krow + e, true);
-  }
-  cp_async_commit();
-  const float2 wbase = cmul(root20(a.T, (uint32_t)id.k1 << (20 - logM)), root20(a.T, (uint32_t)q << (20 - LOGM2)));
-
-  const float fb2 = a.fbias ? 2.f * __ldg(a.fbias + c) : 0.f;
-  row_fft_to_smem<LOGM2>(Arow, ex, ex, q, a.T, rsync);
-  if (a.gspec) {                                                     // keep the spectrum of g for the backward pass
-    float2* G = a.gspec + ((size_t)(a.c0 + ci) * a.B + (r - ci * a.B)) * rowElems + (size_t)id.k1 * M2;
-    static_for<0, 32>([&](auto s_) { constexpr int s = decltype(s_)::value; G[TPR * s + q] = ex[TPR * s + q]; });
-  }
-  cp_async_wait_group<0>();
-  __syncthreads();
-  float2 v[32];
-  static_for<0, 32>([&](auto s_) {
-    constexpr int s = decltype(s_)::value;
-    const int k2 = TPR * s + q;
-    const int pc = (M2 - k2 - id.nz) & (M2 - 1);
-    float2 E, O, He, Ho;
-    even_odd(ex[k2], cconj(exp_[pc]), E, O);
-    even_odd_filter(kg[k2], cconj(kgp[pc]), fb2, He, Ho);
-    const float2 W = mul_w32<s, false>(wbase);
-    float2 Ye = cadd(cmul(E, He), cmul(W, cmul(O, Ho)));
-    float2 Yo = cadd(cmul(E, Ho), cmul(O, He));
-    v[s] = cadd(Ye, cmul_i(Yo));
-  });
-  __syncthreads();                                                   // partner rows are done reading this row's spectrum
-  row_ifft_store<LOGM2>(v, ex, Arow, q, id.k1, logM, a.T, rsync);
 }
 
 template <int MODE, int LOGM2>

@@ -92,31 +92,47 @@ struct Geo {
   __host__ __device__ static constexpr int ex_elems() { return R2 == 1 ? 0 : 32 * P; }
 };
 
-// v[idx(s)] *= base * step^s for s in [0,32), building the powers with <= 4 chained roundings.
+// v[idx(s)] *= lo[s & 7] * hi[s >> 3] for s in [0,32) (hi[0] is taken as 1), the 32 twiddles base * step^s of a geometric
+// sequence split as (base * step^j, j < 8) x (step^{8m}, m < 4).  The callers read all eleven factors straight from the
+// twiddle tables (one or two correctly rounded table entries each), so that every twiddle carries at most one table
+// product and ONE further rounding -- round 1 built them by chained multiplications (up to five roundings), which showed up
+// as ~1.3x the error of the reference's cuFFT path at L = 2^20 (tests/test_gpu_parity_full.py).
 // idx is a constexpr functor s -> register index.  CONJ multiplies by the conjugates instead.
 template <bool CONJ, class IDX>
-__device__ __forceinline__ void mul_geometric(float2 (&v)[32], float2 base, float2 s1, float2 s2, float2 s4,
-                                              float2 s8, float2 s16, IDX) {
-  if (CONJ) { base = cconj(base); s1 = cconj(s1); s2 = cconj(s2); s4 = cconj(s4); s8 = cconj(s8); s16 = cconj(s16); }
-  float2 lo[8];
-  lo[0] = base;
-  lo[1] = cmul(base, s1);
-  lo[2] = cmul(base, s2);
-  lo[3] = cmul(lo[1], s2);
-  lo[4] = cmul(base, s4);
-  lo[5] = cmul(lo[1], s4);
-  lo[6] = cmul(lo[2], s4);
-  lo[7] = cmul(lo[3], s4);
-  const float2 s24 = cmul(s8, s16);
+__device__ __forceinline__ void mul_twiddles(float2 (&v)[32], const float2 (&lo_)[8], const float2 (&hi_)[4], IDX) {
+  float2 lo[8], hi[4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) lo[j] = CONJ ? cconj(lo_[j]) : lo_[j];
+#pragma unroll
+  for (int j = 1; j < 4; ++j) hi[j] = CONJ ? cconj(hi_[j]) : hi_[j];
   static_for<0, 32>([&](auto s_) {
     constexpr int s = decltype(s_)::value;
     constexpr int r = IDX::at(s);
     float2 w = lo[s & 7];
-    if constexpr ((s >> 3) == 1) w = cmul(w, s8);
-    if constexpr ((s >> 3) == 2) w = cmul(w, s16);
-    if constexpr ((s >> 3) == 3) w = cmul(w, s24);
+    if constexpr ((s >> 3) > 0) w = cmul(w, hi[s >> 3]);
     v[r] = cmul(v[r], w);
   });
+}
+
+// W_{2^20}^{(eb + j*es) << sh} for j < 8 and W^{(8 m es) << sh} for m in 1..3, exponents modulo 2^logM
+__device__ __forceinline__ void twiddle_factors20(const Twiddles& T, uint32_t eb, uint32_t es, int logM, float2 (&lo)[8],
+                                                  float2 (&hi)[4]) {
+  const int sh = 20 - logM;
+  const uint32_t mask = (1u << logM) - 1u;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) lo[j] = root20(T, ((eb + (uint32_t)j * es) & mask) << sh);
+  hi[0] = make_float2(1.f, 0.f);
+#pragma unroll
+  for (int m = 1; m < 4; ++m) hi[m] = root20(T, ((8u * (uint32_t)m * es) & mask) << sh);
+}
+
+// the same from the 1024-entry table alone: W_1024^{(j e1)} and W_1024^{(8 m e1)}
+__device__ __forceinline__ void twiddle_factors10(const float2* __restrict__ tw1024, uint32_t e1, float2 (&lo)[8], float2 (&hi)[4]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) lo[j] = __ldg(tw1024 + (((uint32_t)j * e1) & 1023u));
+  hi[0] = make_float2(1.f, 0.f);
+#pragma unroll
+  for (int m = 1; m < 4; ++m) hi[m] = __ldg(tw1024 + ((8u * (uint32_t)m * e1) & 1023u));
 }
 
 template <int LOGN> struct SlotIdx { __host__ __device__ static constexpr int at(int s) { return Geo<LOGN>::slot(s); } };
@@ -138,12 +154,9 @@ __device__ __forceinline__ void block_fft(float2 (&v)[32], float2* ex, int q, co
     // twiddle W_N^{q*k1'}: geometric in k1' with ratio W_N^q; exponents taken from the 1024-table
     constexpr int SH = 10 - LOGN;                         // W_N^e = tw1024[e << SH]
     const uint32_t e1 = (uint32_t)q << SH;
-    float2 s1 = __ldg(tw1024 + (e1 & 1023u));
-    float2 s2 = __ldg(tw1024 + ((2u * e1) & 1023u));
-    float2 s4 = __ldg(tw1024 + ((4u * e1) & 1023u));
-    float2 s8 = __ldg(tw1024 + ((8u * e1) & 1023u));
-    float2 s16 = __ldg(tw1024 + ((16u * e1) & 1023u));
-    mul_geometric<INV>(v, make_float2(1.f, 0.f), s1, s2, s4, s8, s16, Brev5Idx{});
+    float2 lo[8], hi[4];
+    twiddle_factors10(tw1024, e1, lo, hi);
+    mul_twiddles<INV>(v, lo, hi, Brev5Idx{});
     // exchange: ex[k1' * P + q]
     static_for<0, 32>([&](auto k_) {
       constexpr int k1 = decltype(k_)::value;
@@ -162,62 +175,6 @@ __device__ __forceinline__ void block_fft(float2 (&v)[32], float2* ex, int q, co
       dif<G::R2, i * G::R2, INV, 32>(v);
     });
   }
-}
-
-// ------------------------------------------------------------------------------------------
-// 4096-point FFT spread over 128 threads (32 points each): 4096 = 32 x (32 x 4), two exchanges.
-//   in : natural slot s (element 128*s + q) in v[s], q = thread index in [0,128)
-//   out: natural slot s in v[Slot4096::at(s)]
-//   ex : 32*129 complex of shared memory private to this transform; `sync` is a barrier over the
-//        128 threads of the transform.
-struct Slot4096 { __host__ __device__ static constexpr int at(int s) { return 4 * (s % 8) + brev(s / 8, 2); } };
-constexpr int kEx4096 = 32 * 129;
-
-template <bool INV, class SYNC>
-__device__ __forceinline__ void block_fft4096(float2 (&v)[32], float2* ex, int q, const Twiddles& T, SYNC sync) {
-  // stage 1: radix-32 over n1 (stride 128); X1[k1'] in v[brev5(k1')]; twiddle W_4096^{q k1'}
-  dif<32, 0, INV, 32>(v);
-  {
-    const uint32_t e = (uint32_t)q;             // exponents modulo 4096, scaled by 2^8 into the 2^20 tables
-    float2 s1 = root20(T, (e & 4095u) << 8), s2 = root20(T, ((2u * e) & 4095u) << 8),
-           s4 = root20(T, ((4u * e) & 4095u) << 8), s8 = root20(T, ((8u * e) & 4095u) << 8),
-           s16 = root20(T, ((16u * e) & 4095u) << 8);
-    mul_geometric<INV>(v, make_float2(1.f, 0.f), s1, s2, s4, s8, s16, Brev5Idx{});
-  }
-  static_for<0, 32>([&](auto k_) {
-    constexpr int k1 = decltype(k_)::value;
-    ex[k1 * 129 + q] = v[brev(k1, 5)];
-  });
-  sync();
-  // stage 2a: thread (k1' = q & 31, n2'' = q >> 5): radix-32 over n1'' of y[4 n1'' + n2'']; twiddle W_128^{n2'' k1''}
-  const int k1p = q & 31, c = q >> 5;
-  static_for<0, 32>([&](auto n_) {
-    constexpr int n1 = decltype(n_)::value;
-    v[n1] = ex[k1p * 129 + 4 * n1 + c];
-  });
-  sync();                                        // everyone has read before the area is reused
-  dif<32, 0, INV, 32>(v);
-  {
-    const uint32_t e = (uint32_t)c * 8u;        // W_128^c = W_1024^{8c}
-    float2 s1 = __ldg(T.tw1024 + (e & 1023u)), s2 = __ldg(T.tw1024 + ((2u * e) & 1023u)),
-           s4 = __ldg(T.tw1024 + ((4u * e) & 1023u)), s8 = __ldg(T.tw1024 + ((8u * e) & 1023u)),
-           s16 = __ldg(T.tw1024 + ((16u * e) & 1023u));
-    mul_geometric<INV>(v, make_float2(1.f, 0.f), s1, s2, s4, s8, s16, Brev5Idx{});
-  }
-  static_for<0, 32>([&](auto k_) {
-    constexpr int k1 = decltype(k_)::value;
-    ex[k1p * 129 + 4 * k1 + c] = v[brev(k1, 5)];
-  });
-  sync();
-  // stage 2b: thread q owns (k1', k1'' = c + 4j), j < 8: radix-4 over n2''
-  static_for<0, 8>([&](auto j_) {
-    constexpr int j = decltype(j_)::value;
-    static_for<0, 4>([&](auto n_) {
-      constexpr int n = decltype(n_)::value;
-      v[4 * j + n] = ex[k1p * 129 + (c + 4 * j) * 4 + n];
-    });
-  });
-  static_for<0, 8>([&](auto j_) { dif<4, 4 * decltype(j_)::value, INV, 32>(v); });
 }
 
 }  // namespace hy

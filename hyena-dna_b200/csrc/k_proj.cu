@@ -1,0 +1,102 @@
+// Launchers of the tcgen05 projection GEMMs (proj_gemm.cuh).
+#include "launch.h"
+#include "proj_gemm.cuh"
+
+namespace hy {
+
+size_t proj_wimg_bytes(int N, int K) {
+  const int NT = (N % 192 == 0) ? 192 : 128;
+  return pg::wimg_floats(N, K, NT) * sizeof(float);
+}
+
+template <int NT, int ACT, int OUT>
+static cudaError_t go(const pg::Args& a, int sms, cudaStream_t s) {
+  auto kern = pg::proj_gemm_kernel<NT, ACT, OUT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pg::Cfg<NT>::SMEM);
+  if (e != cudaSuccess) return e;
+  const long long ntiles = (long long)a.B * a.mtiles_per_b * a.ntiles_n;
+  const int grid = (int)(ntiles < sms ? ntiles : sms);
+  prof_begin(K_PROJ_GEMM, s);
+  kern<<<grid, pg::kThreads, pg::Cfg<NT>::SMEM, s>>>(a);
+  prof_end(K_PROJ_GEMM, s);
+  return cudaGetLastError();
+}
+
+template <int NT>
+static cudaError_t by_layout(const pg::Args& a, int act_layout, int out_layout, int sms, cudaStream_t s) {
+  if (act_layout == pg::ACT_ROW && out_layout == pg::OUT_CH) return go<NT, pg::ACT_ROW, pg::OUT_CH>(a, sms, s);
+  if (act_layout == pg::ACT_ROW && out_layout == pg::OUT_ROW) return go<NT, pg::ACT_ROW, pg::OUT_ROW>(a, sms, s);
+  if (act_layout == pg::ACT_CH && out_layout == pg::OUT_CH) return go<NT, pg::ACT_CH, pg::OUT_CH>(a, sms, s);
+  if (act_layout == pg::ACT_CH && out_layout == pg::OUT_ROW) return go<NT, pg::ACT_CH, pg::OUT_ROW>(a, sms, s);
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_proj_gemm(const float* act, int act_layout, const float* W, int ldw, int w_transposed, const float* bias,
+                             const float* fir, float* out, int out_layout, int B, int L, int K, int N, int l0, int ln,
+                             float* wimg, cudaStream_t s) {
+  const int NT = (N % 192 == 0) ? 192 : 128;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const size_t total = pg::wimg_floats(N, K, NT);
+  int pblocks = (int)((total + 255) / 256);
+  if (pblocks > 4 * sms) pblocks = 4 * sms;
+  prof_begin(K_PROJ_PREP, s);
+  pg::proj_prep_kernel<<<pblocks, 256, 0, s>>>(W, ldw, w_transposed, N, K, NT, wimg);
+  prof_end(K_PROJ_PREP, s);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  pg::Args a;
+  a.act = act; a.wimg = wimg; a.out = out; a.bias = bias; a.fir = fir;
+  a.B = B; a.L = L; a.K = K; a.N = N; a.l0 = l0; a.ln = ln;
+  a.kchunks = (K + pg::kKC - 1) / pg::kKC;
+  a.ntiles_n = (N + NT - 1) / NT;
+  a.mtiles_per_b = (ln + 127) / 128;
+  return NT == 192 ? by_layout<192>(a, act_layout, out_layout, sms, s) : by_layout<128>(a, act_layout, out_layout, sms, s);
+}
+
+
+// weight gradient: dW (M, N) [or (N, M) when transposed_out] = sum_{b,pos} X[b][m][pos] Y[b][pos][n]
+void proj_wgrad_plan(int M, int N, int sms, int* mtiles, int* ntiles, int* splits) {
+  *mtiles = (M + 127) / 128;
+  *ntiles = (N + 255) / 256;
+  int s = sms / (*mtiles * *ntiles);
+  *splits = s < 1 ? 1 : s;
+}
+
+size_t proj_wgrad_scratch_bytes(int M, int N) {
+  int dev = 0, sms = 148, mt, nt, sp;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  proj_wgrad_plan(M, N, sms, &mt, &nt, &sp);
+  return (size_t)sp * M * N * sizeof(float);
+}
+
+cudaError_t launch_proj_wgrad(const float* X, const float* Y, const float* fir, float* dW, int transposed_out, float beta,
+                              int B, int L, int M, int N, float* part, cudaStream_t s) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  wg::Args a;
+  a.X = X; a.Y = Y; a.fir = fir; a.part = part; a.B = B; a.L = L; a.M = M; a.N = N;
+  a.chunks_per_b = (L + 31) / 32;
+  proj_wgrad_plan(M, N, sms, &a.mtiles, &a.ntiles, &a.splits);
+  const long long total_chunks = (long long)B * a.chunks_per_b;
+  if (a.splits > total_chunks) a.splits = (int)total_chunks;
+  cudaError_t e = cudaFuncSetAttribute(wg::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg::kSmem);
+  if (e != cudaSuccess) return e;
+  prof_begin(K_PROJ_WGRAD, s);
+  wg::wgrad_kernel<<<a.mtiles * a.ntiles * a.splits, wg::kThreads, wg::kSmem, s>>>(a);
+  prof_end(K_PROJ_WGRAD, s);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const size_t total = (size_t)M * N;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 2 * sms) blocks = 2 * sms;
+  prof_begin(K_PROJ_WGRAD, s);
+  wg::wgrad_reduce_kernel<<<blocks, 256, 0, s>>>(part, dW, a.splits, M, N, transposed_out, beta);
+  prof_end(K_PROJ_WGRAD, s);
+  return cudaGetLastError();
+}
+
+}  // namespace hy

@@ -12,7 +12,7 @@ enum Kind {
   K_COL_INV = 4,      // + InvMode  (4..8)
   K_ROW = 9,          // + RowMode  (9..11)
   K_FILTER_FWD = 12, K_FILTER_BWD = 13, K_SHORT_BWD = 14, K_TWIDDLE = 15, K_FILTER_TC_PREP = 16, K_FILTER_TC_FWD = 17,
-  K_FILTER_TC_BWD = 18, K_FILTER_TC_RED = 19, K_FUSED_FWD = 20, K_CONVERT = 21, K_COUNT = 22
+  K_FILTER_TC_BWD = 18, K_FILTER_TC_RED = 19, K_FUSED_FWD = 20, K_CONVERT = 21, K_PROJ_PREP = 22, K_PROJ_GEMM = 23, K_PROJ_WGRAD = 24, K_COUNT = 25
 };
 void prof_begin(int kind, cudaStream_t s);     // api.cu: records an event when profiling is on
 void prof_end(int kind, cudaStream_t s);       // api.cu: records an event when profiling is on; counts the launch
@@ -31,6 +31,14 @@ cudaError_t launch_filter_red_tc(const RedLaunch& r, cudaStream_t s);   // k_fil
 cudaError_t launch_filter_bwd(const FilterParams& P, const float* dk, const FilterGrads& G, cudaStream_t s);
 cudaError_t launch_short_bwd(const ShortBwdArgs& a, int B, cudaStream_t s);
 cudaError_t launch_twiddle_init(float2* tw1024, float2* twlo, cudaStream_t s);
+// k_proj.cu: projection GEMMs on tcgen05 (3xTF32)
+size_t proj_wimg_bytes(int N, int K);
+cudaError_t launch_proj_gemm(const float* act, int act_layout, const float* W, int ldw, int w_transposed, const float* bias,
+                             const float* fir, float* out, int out_layout, int B, int L, int K, int N, int l0, int ln,
+                             float* wimg, cudaStream_t s);
+size_t proj_wgrad_scratch_bytes(int M, int N);
+cudaError_t launch_proj_wgrad(const float* X, const float* Y, const float* fir, float* dW, int transposed_out, float beta,
+                              int B, int L, int M, int N, float* part, cudaStream_t s);
 // k_convert.cu: reference filter-spectrum convention (rfft(k, fft_size), natural order) <-> packed spectrum
 cudaError_t launch_rfft_to_packed(const float2* X, float2* Z, int H, int logM, int logM1, cudaStream_t s);
 cudaError_t launch_packed_to_rfft(const float2* Z, float2* X, int H, int logM, int logM1, float scale, cudaStream_t s);

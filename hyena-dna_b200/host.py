@@ -22,8 +22,9 @@ from ._lib import HyenaB200Error
 
 class HostStep:
     def __init__(self, op, batch, seqlen, chunks=4):
-        if ops.gemm_mode() != "bf16x9":
-            raise HyenaB200Error("HostStep needs the cuBLASLt 12.9 projection path (csrc/gemm.cu)")
+        self.tc = ops.proj_mode() == "tc"               # own tcgen05 projections (default) or cuBLASLt slices
+        if not self.tc and ops.gemm_mode() != "bf16x9":
+            raise HyenaB200Error("HostStep needs the tcgen05 projections or the cuBLASLt 12.9 projection path")
         self.op = op
         dev = op.in_proj.weight.device
         self.dev = dev
@@ -49,18 +50,27 @@ class HostStep:
         B, L, D = self.B, self.L, self.D
         W = self.op.in_proj.weight
         C3 = W.shape[0]
+        if self.tc:
+            ops.proj_gemm(self.u, 0, W, False, 0, out=self.p, l_range=(lo, hi))
+            return
         # P^T[lo:hi] (n x 3D, ld L) = U[lo:hi] (n x D; stored (D x n), ld D -> op T) W^T (D x 3D, stored, op N)
         ops.gemm(1, 0, hi - lo, C3, D, self.u[:, lo:], D, L * D, W, D, 0, self.p[:, :, lo:], L, C3 * L, batch=B)
 
     def _out_proj_chunk(self, y_pre, lo, hi):
         B, L, D = self.B, self.L, self.D
         W, b = self.op.out_proj.weight, self.op.out_proj.bias
+        if self.tc:
+            ops.proj_gemm(y_pre, 1, W, False, 1, bias=b, out=self.y, l_range=(lo, hi))
+            return
         ops.gemm(1, 1, D, hi - lo, D, W, D, 0, y_pre[:, :, lo:], L, D * L, self.y[:, lo:], D, L * D, batch=B, bias=b)
 
     def _du_chunk(self, dp, lo, hi):
         B, L, D = self.B, self.L, self.D
         W = self.op.in_proj.weight
         C3 = W.shape[0]
+        if self.tc:
+            ops.proj_gemm(dp, 1, W, True, 1, out=self.du, l_range=(lo, hi))
+            return
         ops.gemm(0, 1, D, hi - lo, C3, W, D, 0, dp[:, :, lo:], L, C3 * L, self.du[:, lo:], D, L * D, batch=B)
 
     # ------------------------------------------------------------------ one step
@@ -109,11 +119,15 @@ class HostStep:
         # ---- backward
         main.wait_event(ev_dy)
         Wo = op.out_proj.weight
-        # d_pre^T (L x D, ld L) = dY (L x D; stored (D x L) -> op T) Wo (D x D; stored (D x D)^T -> op T)
-        ops.gemm(1, 1, L, D, D, self.dy, D, L * D, Wo, D, 0, self.d_pre, L, D * L, batch=B)
-        dWo = torch.empty_like(Wo)
-        for b in range(B):
-            ops.gemm(1, 1, D, D, L, y_pre[b], L, 0, self.dy[b], D, 0, dWo, D, 0, beta=0.0 if b == 0 else 1.0)
+        if self.tc:
+            ops.proj_gemm(self.dy, 0, Wo, True, 0, out=self.d_pre)
+            dWo = ops.proj_wgrad(y_pre, self.dy, transposed_out=True)
+        else:
+            # d_pre^T (L x D, ld L) = dY (L x D; stored (D x L) -> op T) Wo (D x D; stored (D x D)^T -> op T)
+            ops.gemm(1, 1, L, D, D, self.dy, D, L * D, Wo, D, 0, self.d_pre, L, D * L, batch=B)
+            dWo = torch.empty_like(Wo)
+            for b in range(B):
+                ops.gemm(1, 1, D, D, L, y_pre[b], L, 0, self.dy[b], D, 0, dWo, D, 0, beta=0.0 if b == 0 else 1.0)
         dbo = self.dy.sum((0, 1))
         dp, dk, dsw, dsb, dfb, dib = ops.core_backward(self.d_pre, self.p, ib, sw, sb, kspec, fb, c, gs)
         for lo, hi in self.bounds:                                       # du first, so that it can leave early
@@ -124,9 +138,12 @@ class HostStep:
                 for b in range(B):
                     du_host[b, lo:hi].copy_(self.du[b, lo:hi], non_blocking=True)
         Wi = op.in_proj.weight
-        dWi = torch.empty_like(Wi)
-        for b in range(B):
-            ops.gemm(0, 0, D, 3 * D, L, self.u[b], D, 0, dp[b], L, 0, dWi, D, 0, beta=0.0 if b == 0 else 1.0)
+        if self.tc:
+            dWi = ops.proj_wgrad(dp, self.u)
+        else:
+            dWi = torch.empty_like(Wi)
+            for b in range(B):
+                ops.gemm(0, 0, D, 3 * D, L, self.u[b], D, 0, dp[b], L, 0, dWi, D, 0, beta=0.0 if b == 0 else 1.0)
         need_dz = ff.pos_emb.z.requires_grad
         fgrads, dfreq, dz = ops.filter_backward(*fargs, dk, need_dz)
         # ---- parameter gradients, keyed by parameter identity, then copied out in op.parameters() order
@@ -136,6 +153,10 @@ class HostStep:
              id(f[0].weight): fgrads[0], id(f[0].bias): fgrads[1], id(f[2].weight): fgrads[2],
              id(f[2].bias): fgrads[3], id(f[4].weight): fgrads[4], id(f[4].bias): fgrads[5],
              id(f[6].weight): fgrads[6], id(f[1].freq): dfreq.reshape(f[1].freq.shape)}
+        missing = [n for n, prm in op.named_parameters() if prm.requires_grad and id(prm) not in g
+                   and not (need_dz and prm is ff.pos_emb.z)]
+        if missing:     # e.g. modulation deltas registered as a Parameter (modulation_lr != 0)
+            raise HyenaB200Error(f"HostStep: no gradient is produced for trainable parameter(s) {missing}")
         if need_dz:
             gz = torch.zeros_like(ff.pos_emb.z)
             gz[0, :L].copy_(dz)

@@ -154,7 +154,10 @@ class _InProj(torch.autograd.Function):
         ctx.save_for_backward(u, W)
         B, L, D = u.shape
         C3 = W.shape[0]
-        if ops.gemm_mode() == "torch":
+        mode = ops.proj_mode()
+        if mode == "tc":
+            return ops.proj_gemm(u, 0, W, False, 0)                       # p (B, 3D, L) = W u^T, channel-major
+        if mode == "torch":
             return torch.bmm(W.unsqueeze(0).expand(B, -1, -1), u.transpose(1, 2))
         p = torch.empty(B, C3, L, dtype=torch.float32, device=u.device)
         # col-major: P^T (L x 3D, ld L) = U (L x D) W^T (D x 3D);  U stored (D x L, ld D) -> op T
@@ -167,7 +170,12 @@ class _InProj(torch.autograd.Function):
         B, L, D = u.shape
         C3 = W.shape[0]
         dp = dp.contiguous()
-        if ops.gemm_mode() == "torch":
+        mode = ops.proj_mode()
+        if mode == "tc":
+            du = ops.proj_gemm(dp, 1, W, True, 1) if ctx.needs_input_grad[0] else None      # du = dp^T W
+            dW = ops.proj_wgrad(dp, u) if ctx.needs_input_grad[1] else None                 # dW = sum dp u
+            return du, dW
+        if mode == "torch":
             du = torch.matmul(dp.transpose(1, 2), W) if ctx.needs_input_grad[0] else None
             dW = torch.bmm(dp, u).sum(0) if ctx.needs_input_grad[1] else None
             return du, dW
@@ -201,7 +209,10 @@ class _OutProj(torch.autograd.Function):
         ctx.has_bias = b is not None
         B, C, L = y_pre.shape
         Do = W.shape[0]
-        if ops.gemm_mode() == "torch":
+        mode = ops.proj_mode()
+        if mode == "tc":
+            return ops.proj_gemm(y_pre, 1, W, False, 1, bias=b.contiguous() if b is not None else None)
+        if mode == "torch":
             y = torch.bmm(y_pre.transpose(1, 2), W.t().unsqueeze(0).expand(B, -1, -1))
             if b is not None:
                 y += b
@@ -218,7 +229,13 @@ class _OutProj(torch.autograd.Function):
         B, C, L = y_pre.shape
         Do = W.shape[0]
         dy = dy.contiguous()
-        if ops.gemm_mode() == "torch":
+        mode = ops.proj_mode()
+        if mode == "tc":
+            d_pre = ops.proj_gemm(dy, 0, W, True, 0) if ctx.needs_input_grad[0] else None          # (B, C, L) = W^T dy^T
+            dW = ops.proj_wgrad(y_pre, dy, transposed_out=True) if ctx.needs_input_grad[1] else None   # (Do, C)
+            db = dy.sum((0, 1)) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+            return d_pre, dW, db
+        if mode == "torch":
             d_pre = torch.bmm(W.t().unsqueeze(0).expand(B, -1, -1), dy.transpose(1, 2)) if ctx.needs_input_grad[0] else None
             dW = torch.bmm(dy.transpose(1, 2), y_pre.transpose(1, 2)).sum(0) if ctx.needs_input_grad[1] else None
             db = dy.sum((0, 1)) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
@@ -291,12 +308,17 @@ class HyenaOperator(nn.Module):
         u = u.to(torch.float32)
         l = u.size(-2)
         l_filter = min(l, self.l_max)
-        p = _InProj.apply(u, self.in_proj.weight)                                   # (B, 3D, l)
-        if l_filter < l:
-            p = p[..., :l_filter].contiguous()
         k = self.filter_fn.filter_channel_major(l_filter)                           # (D, l_filter)
         fb = self.filter_fn.bias if self.filter_fn.use_bias else 0 * self.filter_fn.bias
-        y_pre = ops.HyenaCoreFn.apply(p, self.in_proj.bias, self.short_filter.weight, self.short_filter.bias, k, fb)
+        if ops.proj_mode() == "tc" and l_filter == l and ops.fuse_fir():
+            # one autograd node: in_proj GEMM + fused core; backward feeds ds straight into the projection GEMMs
+            y_pre = ops.HyenaInCoreFn.apply(u, self.in_proj.weight, self.in_proj.bias, self.short_filter.weight,
+                                            self.short_filter.bias, k, fb)
+        else:
+            p = _InProj.apply(u, self.in_proj.weight)                               # (B, 3D, l)
+            if l_filter < l:
+                p = p[..., :l_filter].contiguous()
+            y_pre = ops.HyenaCoreFn.apply(p, self.in_proj.bias, self.short_filter.weight, self.short_filter.bias, k, fb)
         y = _OutProj.apply(y_pre, self.out_proj.weight, self.out_proj.bias).to(in_dtype)
         if self.return_state:
             return y, None

@@ -242,7 +242,7 @@ def core_forward(p, in_bias, sw, sb, kspec, fbias, save_c):
     return y, c, gs
 
 
-def core_backward(dy_pre, p, in_bias, sw, sb, kspec, fbias, c_saved, gspec=None):
+def core_backward(dy_pre, p, in_bias, sw, sb, kspec, fbias, c_saved, gspec=None, return_ds=False):
     _need_cuda(dy_pre, p, in_bias, sw, sb, fbias, c_saved)
     B, C3, L = p.shape
     D = C3 // 3
@@ -251,7 +251,7 @@ def core_backward(dy_pre, p, in_bias, sw, sb, kspec, fbias, c_saved, gspec=None)
     if tuple(dy_pre.shape) != (B, D, L) or tuple(c_saved.shape) != (B, D, L):
         raise _lib.HyenaB200Error("core_backward: dy_pre / c_saved must be (B, D, L)")
     dy_pre = dy_pre.contiguous()
-    dp = torch.empty_like(p)
+    dp = None if return_ds else torch.empty_like(p)
     ds = torch.empty_like(p)
     dk = torch.empty(D, L, dtype=torch.float32, device=dev)
     dsw = torch.zeros(C3, 3, dtype=torch.float32, device=dev)
@@ -264,6 +264,13 @@ def core_backward(dy_pre, p, in_bias, sw, sb, kspec, fbias, c_saved, gspec=None)
             _ptr(dy_pre), _ptr(p), _ptr(in_bias), _ptr(sw), _ptr(sb), _ptr(kspec), _ptr(fbias), _ptr(c_saved),
             _ptr(gspec), _ptr(dp), _ptr(dk), _ptr(dsw), _ptr(dsb), _ptr(dfb), _ptr(dib), _ptr(ds),
             B, D, L, _ptr(ws), ws.numel(), _stream()))
+    if return_ds:
+        # d in_proj.bias = sum_t dp[t] = (w0 + w1 + w2) sum_t ds[t] - w1 ds[0] - w0 (ds[0] + ds[1])   (conv padding edge)
+        if in_bias is not None:
+            e0 = ds[:, :, 0].sum(0)
+            e1 = ds[:, :, 1].sum(0) if L > 1 else torch.zeros_like(e0)
+            dib = sw.sum(1) * dsb - sw[:, 1] * e0 - sw[:, 0] * (e0 + e1)
+        return ds, dk, dsw, dsb, dfb, dib
     del ds
     return dp, dk, dsw, dsb, dfb, dib
 
@@ -289,6 +296,36 @@ class HyenaCoreFn(torch.autograd.Function):
         p, ib, sw2, sb, kspec, fbias, c, gs = ctx.saved_tensors
         dp, dk, dsw, dsb, dfb, dib = core_backward(dy, p, ib, sw2, sb, kspec, fbias, c, gs)
         return dp, dib, dsw.reshape(ctx.sw_shape), dsb, dk, dfb
+
+
+class HyenaInCoreFn(torch.autograd.Function):
+    """in_proj + operator core as ONE autograd node (tcgen05 projections): u (B, L, D) -> y_pre (B, D, L).
+
+    Forward: p = W u^T channel-major (proj_gemm), then the fused core.  Backward: the core returns ds (gradient w.r.t. the
+    short-filter outputs) and the two projection-backward GEMMs apply the transposed 3-tap filter to it on the fly, so
+    neither dp nor a separate short-filter backward pass exists (hyena.py:391-432 and its autograd)."""
+
+    @staticmethod
+    def forward(ctx, u, W, in_bias, sw, sb, k, fbias):
+        u = u.contiguous(); W = W.contiguous()
+        sw2 = sw.reshape(sw.shape[0], -1).contiguous()
+        sb = sb.contiguous(); fbias = fbias.contiguous()
+        ib = in_bias.contiguous() if in_bias is not None else None
+        p = proj_gemm(u, 0, W, False, 0)
+        kspec = filter_spectrum(k)
+        need = any(ctx.needs_input_grad)
+        y, c, gs = core_forward(p, ib, sw2, sb, kspec, fbias, need)
+        ctx.save_for_backward(u, W, p, ib, sw2, sb, kspec, fbias, c, gs)
+        ctx.sw_shape = sw.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        u, W, p, ib, sw2, sb, kspec, fbias, c, gs = ctx.saved_tensors
+        ds, dk, dsw, dsb, dfb, dib = core_backward(dy, p, ib, sw2, sb, kspec, fbias, c, gs, return_ds=True)
+        du = proj_gemm(ds, 1, W, True, 1, fir=sw2) if ctx.needs_input_grad[0] else None
+        dW = proj_wgrad(ds, u, fir=sw2) if ctx.needs_input_grad[1] else None
+        return du, dW, dib, dsw.reshape(ctx.sw_shape), dsb, dk, dfb
 
 
 # ------------------------------------------------------------------------------------------ plain fftconv
@@ -365,6 +402,91 @@ def gemm(transa, transb, m, n, k, A, lda, strideA, B, ldb, strideB, C, ldc, stri
                                               _ptr(B), ldb, strideB, float(beta), _ptr(C), ldc, strideC, batch,
                                               _ptr(bias), int(emulate), _ptr(ws), ws.numel(), _stream()))
     return C
+
+
+_wimg_cache = {}
+_proj_mode = None
+
+
+def proj_mode():
+    """'tc': the projections run on this library's tcgen05 3xTF32 kernels (csrc/proj_gemm.cuh) -- the default;
+    'lt': cuBLASLt 12.9 BF16x9 (csrc/gemm.cu; also what runs when the user opted into TF32 via
+    torch.backends.cuda.matmul.allow_tf32); 'torch': torch.bmm.  HYENA_B200_PROJ selects."""
+    global _proj_mode
+    if _proj_mode is None:
+        import os
+        want = os.environ.get("HYENA_B200_PROJ", "tc")
+        if want == "tc":
+            _proj_mode = "tc"
+        else:
+            _proj_mode = "lt" if (want != "torch" and gemm_mode() == "bf16x9") else "torch"
+    if _proj_mode == "tc" and torch.backends.cuda.matmul.allow_tf32 and gemm_mode() == "bf16x9":
+        return "lt"          # plain-TF32 opt-in: one MMA per product on the library path
+    return _proj_mode
+
+
+def proj_gemm(act, act_layout, W, w_transposed, out_layout, bias=None, fir=None, out=None, l_range=None):
+    """OUT[pos][n] = sum_k ACT[pos][k] Wl[n][k] (+ bias) on this library's tcgen05 kernel (csrc/proj_gemm.cuh, 3xTF32).
+    act_layout 0: act (B, L, K); 1: act (B, K, L).  out_layout 0: (B, N, L); 1: (B, L, N).  Wl = W.T if w_transposed."""
+    _need_cuda(act, W, bias, fir)
+    if act.dim() != 3 or W.dim() != 2 or not act.is_contiguous() or not W.is_contiguous():
+        raise _lib.HyenaB200Error("proj_gemm: act must be contiguous 3-D, W contiguous 2-D")
+    B = act.shape[0]
+    L, K = (act.shape[1], act.shape[2]) if act_layout == 0 else (act.shape[2], act.shape[1])
+    N = W.shape[1] if w_transposed else W.shape[0]
+    if (W.shape[0] if w_transposed else W.shape[1]) != K:
+        raise _lib.HyenaB200Error(f"proj_gemm: weight {tuple(W.shape)} does not match K = {K}")
+    dev = act.device
+    oshape = (B, N, L) if out_layout == 0 else (B, L, N)
+    if out is None:
+        out = torch.empty(oshape, dtype=torch.float32, device=dev)
+    elif tuple(out.shape) != oshape or not out.is_contiguous() or out.dtype != torch.float32:
+        raise _lib.HyenaB200Error(f"proj_gemm: out must be contiguous fp32 {oshape}")
+    l0, ln = (0, 0) if l_range is None else (int(l_range[0]), int(l_range[1] - l_range[0]))
+    need = int(_lib.lib().hyena_b200_proj_wimg_bytes(N, K))
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), _stream())
+    wimg = _wimg_cache.get(key)
+    if wimg is None or wimg.numel() < need:
+        wimg = torch.empty(max(need, 4 << 20), dtype=torch.uint8, device=dev)
+        _wimg_cache[key] = wimg
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().hyena_b200_proj_gemm(
+            _ptr(act), int(act_layout), _ptr(W), W.shape[1], int(bool(w_transposed)), _ptr(bias), _ptr(fir), _ptr(out),
+            int(out_layout), B, L, K, N, l0, ln, _ptr(wimg), wimg.numel(), _stream()))
+    return out
+
+
+_wgrad_cache = {}
+
+
+def fuse_fir():
+    """Transposed short filter fused into the projection-backward GEMMs (default on; HYENA_B200_FUSE_FIR=0 keeps the
+    separate short_conv_bwd pass for A/B runs)."""
+    import os
+    return os.environ.get("HYENA_B200_FUSE_FIR", "1") != "0"
+
+
+def proj_wgrad(X, Y, fir=None, transposed_out=False):
+    """dW (M, N) [(N, M) if transposed_out] = sum_{b,pos} X[b][m][pos] Y[b][pos][n]; X (B, M, L), Y (B, L, N)
+    (csrc/proj_gemm.cuh wgrad_kernel: tcgen05 3xTF32, split-K, deterministic)."""
+    _need_cuda(X, Y, fir)
+    if X.dim() != 3 or Y.dim() != 3 or not X.is_contiguous() or not Y.is_contiguous() or X.shape[0] != Y.shape[0] \
+            or X.shape[2] != Y.shape[1]:
+        raise _lib.HyenaB200Error(f"proj_wgrad: X (B, M, L) / Y (B, L, N) expected, got {tuple(X.shape)} / {tuple(Y.shape)}")
+    B, M, L = X.shape
+    N = Y.shape[2]
+    dev = X.device
+    dW = torch.empty((N, M) if transposed_out else (M, N), dtype=torch.float32, device=dev)
+    need = int(_lib.lib().hyena_b200_proj_wgrad_scratch_bytes(M, N))
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), _stream())
+    sc = _wgrad_cache.get(key)
+    if sc is None or sc.numel() < need:
+        sc = torch.empty(need, dtype=torch.uint8, device=dev)
+        _wgrad_cache[key] = sc
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().hyena_b200_proj_wgrad(_ptr(X), _ptr(Y), _ptr(fir), _ptr(dW), int(bool(transposed_out)), 0.0,
+                                                    B, L, M, N, _ptr(sc), sc.numel(), _stream()))
+    return dW
 
 
 _side_streams = {}

@@ -121,7 +121,9 @@ HY_API int hyena_b200_core_fwd(const float* p, const float* in_bias, const float
 /* backward of core_fwd (closed form: hyena.py:43-56 FFTConvFuncv2.backward,
  * csrc/fftconv/fftconv_cuda.cu:1157-1179).  dy_pre (B,D,L).  Outputs: dp (B,3D,L), dk (D,L);
  * (+=): dsw (3D,3), dsb (3D), dfbias (D), d_in_bias (3D, may be NULL).
- * ds_scratch (B,3D,L) is caller-provided scratch for the short-filter output grads. */
+ * ds_scratch (B,3D,L) receives ds, the gradient w.r.t. the short-filter OUTPUTS.  With dp == NULL the transposed short
+ * filter pass is skipped (d_in_bias is then not written): hand ds to hyena_b200_proj_gemm / hyena_b200_proj_wgrad with
+ * fir = sw, which apply dp[t] = w2 ds[t] + w1 ds[t+1] + w0 ds[t+2] in registers. */
 HY_API int hyena_b200_core_bwd(const float* dy_pre, const float* p, const float* in_bias, const float* sw,
                         const float* sb, const float* kspec, const float* fbias, const float* c_saved,
                         const float* gspec_saved /* from core_fwd, or NULL to recompute */,
@@ -160,6 +162,33 @@ HY_API int hyena_b200_spectrum_to_rfft(const float* dk, int fft_size, float* dfi
  * on bf16 tensor cores, fp32-level accuracy).  Column-major, strided-batched:
  * C[m,n] = alpha * op(A) op(B) + beta * C (+ bias[m]); op: 0 = N, 1 = T. */
 HY_API int hyena_b200_gemm_available(void);
+
+/* ---- projections on this library's own tensor-core kernel (csrc/proj_gemm.cuh) --------------------
+ * The same GEMMs as above without the library call: tcgen05 / TMEM, fp32 accuracy through 3xTF32, weights streamed by
+ * TMA bulk copies, the activation converted on the fly into tensor memory.  Computes, for every batch b,
+ *     OUT[pos][n] = sum_k ACT[pos][k] * Wl[n][k] (+ bias[n]),    Wl[n][k] = w_transposed ? W[k*ldw + n] : W[n*ldw + k]
+ *   act_layout 0: ACT is (B, L, K) row-major (u, dy: hyena.py:391, :440 backward)
+ *              1: ACT is (B, K, L) channel-major (y_pre, ds: hyena.py:432-440)
+ *   out_layout 0: OUT is (B, N, L) channel-major (p, dy_pre);   1: OUT is (B, L, N) row-major (y, du)
+ *   fir (K,3) non-NULL (act_layout 1 only): ACT is ds, the gradient w.r.t. the short-filter OUTPUT, and the GEMM consumes
+ *              dp[k][t] = fir[k][2] ds[k][t] + fir[k][1] ds[k][t+1] + fir[k][0] ds[k][t+2] (backward of the depthwise
+ *              Conv1d, hyena.py:363-369) computed in registers -- dp never exists in HBM.
+ *   l_begin, l_len: only positions [l_begin, l_begin + l_len) of every batch are computed (host-side pipelining of a
+ *              long sequence against PCIe copies, hyena-dna_b200/host.py); l_len <= 0 means all L positions.
+ *   wimg: scratch of hyena_b200_proj_wimg_bytes(N, K) bytes (tf32 hi/lo images of the weights, rebuilt every call). */
+/* Weight gradients of the projections (hyena.py:391, :440 backward), reduction over the sequence positions:
+ *     dW[m][n] (= or +=) sum_{b,pos} X[b][m][pos] * Y[b][pos][n]
+ * X (B, M, L) channel-major (ds / y_pre), Y (B, L, N) row-major (u / dy); split-K over the SMs with the accumulators in
+ * tensor memory, deterministic reduction of the partials.  transposed_out: dW is stored (N, M).  beta: 0 overwrite, else
+ * dW = beta * dW + sum.  fir (M,3): X is ds and the transposed short filter is applied on the fly (see proj_gemm).
+ * scratch: hyena_b200_proj_wgrad_scratch_bytes(M, N) bytes. */
+HY_API size_t hyena_b200_proj_wgrad_scratch_bytes(int M, int N);
+HY_API int hyena_b200_proj_wgrad(const float* X, const float* Y, const float* fir, float* dW, int transposed_out, float beta,
+                          int B, int L, int M, int N, void* scratch, size_t scratch_bytes, void* stream);
+HY_API size_t hyena_b200_proj_wimg_bytes(int N, int K);
+HY_API int hyena_b200_proj_gemm(const float* act, int act_layout, const float* W, int ldw, int w_transposed,
+                         const float* bias, const float* fir, float* out, int out_layout, int B, int L, int K, int N,
+                         int l_begin, int l_len, void* wimg, size_t wimg_bytes, void* stream);
 HY_API int hyena_b200_gemm(int transa, int transb, int m, int n, int k, float alpha, const float* A, int lda,
                            long long strideA, const float* B, int ldb, long long strideB, float beta, float* C,
                            int ldc, long long strideC, int batch, const float* bias, int emulate, void* workspace,

@@ -275,7 +275,7 @@ def test_projection_gemms_match_fp64():
     W = (torch.randn(3 * D, D, generator=g) * 0.05).to(dev).requires_grad_(True)
     p = hy._InProj.apply(u, W)
     ref = torch.matmul(W.double(), u.double().transpose(1, 2))
-    _close(p, ref, f"in_proj ({H.ops.gemm_mode()})")
+    _close(p, ref, f"in_proj ({H.ops.proj_mode()})")
     dp = torch.randn(B, 3 * D, L, generator=g).to(dev)
     p.backward(dp)
     _close(u.grad, torch.matmul(dp.double().transpose(1, 2), W.double()), "in_proj du")
@@ -298,8 +298,8 @@ def test_host_step_matches_autograd(B, L, D):
     """HostStep (pinned host buffers, pipelined copies) == module forward + autograd backward."""
     import hyena_dna_b200 as H
     dev = _dev()
-    if H.ops.gemm_mode() != "bf16x9":
-        pytest.skip("needs the cuBLASLt 12.9 projection path")
+    if H.ops.proj_mode() != "tc" and H.ops.gemm_mode() != "bf16x9":
+        pytest.skip("needs the tcgen05 or the cuBLASLt 12.9 projection path")
     torch.manual_seed(5)
     op = H.HyenaOperator(D, L, emb_dim=5, w=10.0, lr_pos_emb=0.0).to(dev)
     u = torch.randn(B, L, D); dy = torch.randn(B, L, D)
@@ -458,3 +458,60 @@ def test_validation_of_spectrum_and_filter_shapes():
     f = H.HyenaFilter(8, emb_dim=5, order=64, seq_len=128, w=10.0).to(dev)
     with pytest.raises(H.HyenaB200Error):          # filter longer than the positional embedding
         f.filter(129)
+
+
+# ------------------------------------------------------------------------------------------ own projection GEMM
+@pytest.mark.parametrize("B,L,K,N", [(1, 128, 32, 128), (2, 1000, 64, 192), (1, 4096, 256, 768), (2, 777, 24, 8),
+                                     (1, 2048, 768, 256), (1, 333, 40, 200)])
+def test_proj_gemm_tcgen05_matches_fp64(B, L, K, N):
+    """csrc/proj_gemm.cuh (tcgen05, 3xTF32, A operand in tensor memory) against float64 matmuls, all four layout
+    combinations, bias epilogue, ragged shapes, and the fused transposed short filter."""
+    import hyena_dna_b200 as H
+    dev = _dev()
+    g = torch.Generator().manual_seed(L + K + N)
+    W = (torch.randn(N, K, generator=g) * 0.05)
+    bias = torch.randn(N, generator=g)
+    for act_layout in (0, 1):
+        act = torch.randn((B, L, K) if act_layout == 0 else (B, K, L), generator=g)
+        a64 = act.double() if act_layout == 0 else act.double().transpose(1, 2)          # (B, L, K)
+        for out_layout in (0, 1):
+            for wt in (False, True):
+                Wd = W.t().contiguous() if wt else W
+                ref = torch.matmul(a64, W.double().t()) + bias.double()                      # (B, L, N)
+                if out_layout == 0:
+                    ref = ref.transpose(1, 2)
+                got = H.ops.proj_gemm(act.to(dev), act_layout, Wd.to(dev), wt, out_layout, bias=bias.to(dev))
+                _close(got, ref, f"proj_gemm act{act_layout} out{out_layout} wt{wt} {B}x{L}x{K}x{N}")
+    # fused transposed FIR on a channel-major activation
+    ds = torch.randn(B, K, L, generator=g)
+    taps = torch.randn(K, 3, generator=g)
+    dsp = torch.nn.functional.pad(ds.double(), (0, 2))
+    dp = taps[:, 2].double()[None, :, None] * dsp[..., :L] + taps[:, 1].double()[None, :, None] * dsp[..., 1:L + 1] \
+        + taps[:, 0].double()[None, :, None] * dsp[..., 2:L + 2]
+    ref = torch.matmul(dp.transpose(1, 2), W.double().t())
+    got = H.ops.proj_gemm(ds.to(dev), 1, W.to(dev), False, 1, fir=taps.to(dev))
+    _close(got, ref, f"proj_gemm fused FIR {B}x{L}x{K}x{N}")
+
+
+@pytest.mark.parametrize("B,L,M,N", [(1, 64, 128, 256), (2, 1000, 192, 64), (1, 40000, 768, 256), (2, 777, 24, 8),
+                                     (1, 5000, 256, 256), (1, 333, 200, 320)])
+def test_proj_wgrad_tcgen05_matches_fp64(B, L, M, N):
+    """Split-K weight-gradient GEMM (MN-major B operand, A in tensor memory) against float64, plain and with the fused
+    transposed short filter, normal and transposed output."""
+    import hyena_dna_b200 as H
+    dev = _dev()
+    g = torch.Generator().manual_seed(L + M + N)
+    X = torch.randn(B, M, L, generator=g)
+    Y = torch.randn(B, L, N, generator=g)
+    ref = torch.einsum("bml,bln->mn", X.double(), Y.double())
+    got = H.ops.proj_wgrad(X.to(dev), Y.to(dev))
+    _close(got, ref, f"wgrad {B}x{L}x{M}x{N}")
+    got_t = H.ops.proj_wgrad(X.to(dev), Y.to(dev), transposed_out=True)
+    _close(got_t, ref.t(), f"wgrad transposed {B}x{L}x{M}x{N}")
+    taps = torch.randn(M, 3, generator=g)
+    Xp = torch.nn.functional.pad(X.double(), (0, 2))
+    dp = taps[:, 2].double()[None, :, None] * Xp[..., :L] + taps[:, 1].double()[None, :, None] * Xp[..., 1:L + 1] \
+        + taps[:, 0].double()[None, :, None] * Xp[..., 2:L + 2]
+    ref_f = torch.einsum("bml,bln->mn", dp, Y.double())
+    got_f = H.ops.proj_wgrad(X.to(dev), Y.to(dev), fir=taps.to(dev))
+    _close(got_f, ref_f, f"wgrad fused FIR {B}x{L}x{M}x{N}")
