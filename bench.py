@@ -139,7 +139,7 @@ def kernel_algorithmic_bytes(B, D, L):
         "row_pass<filter>": 8 * f,                       # kspec out
         "row_pass<conv_fwd>": 8 * f + 8 * n,             # kspec in, saved g spectrum out
         "row_pass<conv_bwd>": 8 * f + 8 * n,             # kspec in, saved g spectrum in
-        "col_inv<conv_fwd>": 20 * n,                     # x0,x1,v in; y_pre, c out
+        "col_inv<conv_fwd>": 12 * n,                     # x0 in; y_pre, c out (the skip term lives in the filter spectrum)
         "col_inv<bwd_dg>": 32 * n,                       # x0,x1,v, dy_pre, c in; ds (3 rows) out
         "col_inv<dk>": 4 * f,                            # dk out
         "short_conv_bwd": 24 * n,                        # ds in, dp out
@@ -161,6 +161,10 @@ def build_roofline(prof, steps, B, D, L, ms_step):
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     span_bytes = (44.0 + 16.0 / B) * D * B * L               # SURVEY.md S8(d), per step
+    # the projections are this library's kernels too now (csrc/proj_gemm.cuh) but sit OUTSIDE the span of S8(d)
+    # (in_proj output -> out_proj input): reported on their own, against the tensor-core roofline
+    proj = {k: v for k, v in prof.items() if k.startswith("proj_")}
+    prof = {k: v for k, v in prof.items() if not k.startswith("proj_")}
     tot_ms = sum(v[0] for v in prof.values())
     span_ms = tot_ms / steps
     achieved = span_bytes / (span_ms * 1e-3) / 1e9 if span_ms > 0 else 0.0
@@ -183,7 +187,20 @@ def build_roofline(prof, steps, B, D, L, ms_step):
             traffic, traffic_src = tj["span_dram_bytes_per_step"], tj["source"]
     except Exception:
         pass
+    projections = None
+    if proj:
+        pms = sum(v[0] for v in proj.values()) / steps
+        flops = 3 * 2.0 * B * L * D * (3 * D + D)            # fwd + input grads + weight grads of in_proj and out_proj
+        tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+        projections = {"ms_per_step": round(pms, 4), "fp32_equivalent_tflops": round(flops / (pms * 1e-3) / 1e12, 1),
+                       "tf32_mma_tflops": round(3 * flops / (pms * 1e-3) / 1e12, 1),
+                       "peak_tf32_dense_tflops_derived": round(tf / 2, 1),
+                       "frac_of_tf32_peak": round(3 * flops / (pms * 1e-3) / 1e12 / (tf / 2), 4),
+                       "note": "3xTF32: three tf32 MMAs per fp32 product; tf32 peak taken as half the measured bf16 peak",
+                       "kernels": {k: {"ms_per_step": round(v[0] / steps, 4), "launches_per_step": v[1] / steps}
+                                   for k, v in proj.items()}}
     return {"bound": "hbm", "kernel": "custom-kernel span (in_proj output -> out_proj input), fwd+bwd, per step",
+            "projections": projections,
             "achieved": round(achieved, 1), "peak": peak_gbs, "unit": "GB/s",
             "frac": round(achieved / peak_gbs, 4), "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": peak_src, "algorithmic_bytes_per_step": span_bytes, "span_ms_per_step": round(span_ms, 4),
@@ -318,6 +335,31 @@ def gpu_reference_run(op, u, dy, steps=3, warmup=1):
             "warmup": warmup, "impl": which, "dtype": "f32, TF32 off"}
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this process (and hence the pinned host buffers it allocates next, first touch) to the CPUs of the NUMA node
+    the GPU hangs off: with 8 ranks x 4.3 GB of PCIe traffic per step the e2e leg otherwise crosses the socket
+    interconnect for half the GPUs (e2e scaling 0.665 at N = 8).  Best effort; returns a note for the line."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bus.startswith("0000"):
+            bus = bus[4:]                                       # sysfs uses a 4-digit domain
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return "numa: single node"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"numa: GPU {local} on node {node}, process bound to its {len(allowed)} CPUs"
+        return f"numa: node {node} has no allowed CPUs"
+    except Exception as e:
+        return f"numa: not bound ({type(e).__name__})"
+
+
 # ----------------------------------------------------------------------------------------- GPU arm
 def main():
     args = parse()
@@ -334,6 +376,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU path for the product arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_note = bind_to_gpu_numa_node(local)
     if world > 1:
         # NCCL prints its version banner with printf on stdout when the environment sets NCCL_DEBUG; stdout must carry
         # exactly one JSON line, so communicator creation (eager with device_id, plus one barrier) runs with fd 1
@@ -372,14 +415,19 @@ def main():
     u = u_host.to(dev).requires_grad_(True)
     dy = dy_host.to(dev)
 
+    # N > 1: two-bucket gradient all-reduce driven by autograd hooks; the first (large) bucket is reduced on a side stream
+    # while the filter backward still runs (hyena-dna_b200/distributed.py)
+    reducer = H.distributed.OverlappedGradReducer(params, named=[(n, p) for n, p in op.named_parameters()
+                                                                 if p.requires_grad]) if world > 1 else None
+
     def step():
         for p in params:
             p.grad = None
         u.grad = None
         y = op(u)
         y.backward(dy)
-        if world > 1:
-            H.distributed.allreduce_grads(params)
+        if reducer is not None:
+            reducer.finish()
         return y
 
     sampler = ClockSampler(local)
@@ -487,7 +535,7 @@ def main():
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(L, D, B, world),
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": int(launches), "host_affinity": numa_note, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_reference": gpu_ref,
                 "speedup_vs_gpu_reference": (gpu_ref or {}).get("speedup"),
                 "tf32_projections_ms_per_step": tf32_ms,

@@ -87,16 +87,6 @@ __device__ __forceinline__ void store_pair(float* __restrict__ row, int t0, int 
 // flight at once, 272-byte contiguous pieces per row) and the math then reads shared memory.
 // Requires L % 4 == 0 and 16-byte aligned rows (PassArgs.stage); otherwise the register path is used.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  const int n = valid ? 16 : 0;                      // src-size 0: the 16 bytes are zero-filled
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 // rows [row0, row0+nrows) x columns [colbase, colbase+C) of the packed row `prow` (L floats), with a 4-float
 // halo on the left (the 3-tap filter reaches back two samples).  dst pitch: 2C+4 floats.
 template <int C, int M2>

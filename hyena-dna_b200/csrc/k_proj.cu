@@ -12,12 +12,14 @@ size_t proj_wimg_bytes(int N, int K) {
 template <int NT, int ACT, int OUT>
 static cudaError_t go(const pg::Args& a, int sms, cudaStream_t s) {
   auto kern = pg::proj_gemm_kernel<NT, ACT, OUT>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pg::Cfg<NT>::SMEM);
+  const size_t smem = pg::Cfg<NT>::SMEM + (a.fir ? (size_t)a.K * 12 : 0);
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const long long ntiles = (long long)a.B * a.mtiles_per_b * a.ntiles_n;
   const int grid = (int)(ntiles < sms ? ntiles : sms);
   prof_begin(K_PROJ_GEMM, s);
-  kern<<<grid, pg::kThreads, pg::Cfg<NT>::SMEM, s>>>(a);
+  kern<<<grid, pg::kThreads, smem, s>>>(a);
   prof_end(K_PROJ_GEMM, s);
   return cudaGetLastError();
 }
@@ -49,6 +51,8 @@ cudaError_t launch_proj_gemm(const float* act, int act_layout, const float* W, i
   pg::Args a;
   a.act = act; a.wimg = wimg; a.out = out; a.bias = bias; a.fir = fir;
   a.B = B; a.L = L; a.K = K; a.N = N; a.l0 = l0; a.ln = ln;
+  if (act_layout == pg::ACT_ROW) a.vec = (K % 4 == 0);
+  else a.vec = (L % 4 == 0) && (l0 % 4 == 0) && (ln % 4 == 0);
   a.kchunks = (K + pg::kKC - 1) / pg::kKC;
   a.ntiles_n = (N + NT - 1) / NT;
   a.mtiles_per_b = (ln + 127) / 128;
@@ -59,7 +63,7 @@ cudaError_t launch_proj_gemm(const float* act, int act_layout, const float* W, i
 // weight gradient: dW (M, N) [or (N, M) when transposed_out] = sum_{b,pos} X[b][m][pos] Y[b][pos][n]
 void proj_wgrad_plan(int M, int N, int sms, int* mtiles, int* ntiles, int* splits) {
   *mtiles = (M + 127) / 128;
-  *ntiles = (N + 255) / 256;
+  *ntiles = (N + 127) / 128;
   int s = sms / (*mtiles * *ntiles);
   *splits = s < 1 ? 1 : s;
 }
@@ -83,6 +87,7 @@ cudaError_t launch_proj_wgrad(const float* X, const float* Y, const float* fir, 
   proj_wgrad_plan(M, N, sms, &a.mtiles, &a.ntiles, &a.splits);
   const long long total_chunks = (long long)B * a.chunks_per_b;
   if (a.splits > total_chunks) a.splits = (int)total_chunks;
+  a.vec = (L % 4 == 0) && (N % 4 == 0);
   cudaError_t e = cudaFuncSetAttribute(wg::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg::kSmem);
   if (e != cudaSuccess) return e;
   prof_begin(K_PROJ_WGRAD, s);

@@ -113,11 +113,26 @@ class HyenaFilter(OptimModule):
                 setattr(getattr(c, name), "_optim", {"weight_decay": wd, "lr": lr})
 
     def filter_channel_major(self, L):
-        """k (D, L): the layout the convolution kernels consume."""
+        """k (D, L): the layout the convolution kernels consume.
+
+        With ``self.cache_filter`` set (see stack.CheckpointedHyenaStack) the generated filter is kept and reused while
+        none of the tensors it depends on has changed (torch's per-tensor version counters: an optimizer step or any
+        in-place write invalidates it).  Under activation checkpointing every layer's forward runs twice per step
+        (long_conv_lm.py:39-45,196-199): the recompute then skips the filter kernels -- at batch 1 they are a third of
+        the custom-kernel time of a forward."""
         f = self.implicit_filter
-        return ops.HyenaFilterFn.apply(self.pos_emb.z, self.pos_emb.t, f[0].weight, f[0].bias, f[2].weight, f[2].bias,
-                                       f[4].weight, f[4].bias, f[6].weight, f[1].freq, self.modulation.deltas,
-                                       float(self.modulation.shift), bool(self.modulate), int(L))
+        args = (self.pos_emb.z, self.pos_emb.t, f[0].weight, f[0].bias, f[2].weight, f[2].bias, f[4].weight, f[4].bias,
+                f[6].weight, f[1].freq, self.modulation.deltas)
+        cached = None
+        if getattr(self, "cache_filter", False):
+            key = (int(L), float(self.modulation.shift), bool(self.modulate)) + tuple((a.data_ptr(), a._version) for a in args)
+            c = getattr(self, "_filter_cache", None)
+            if c is not None and c[0] == key:
+                cached = c[1]
+        k = ops.HyenaFilterFn.apply(*args, float(self.modulation.shift), bool(self.modulate), int(L), cached)
+        if getattr(self, "cache_filter", False) and cached is None:
+            self._filter_cache = (key, k.detach())
+        return k
 
     def filter(self, L, *args, **kwargs):
         return self.filter_channel_major(L).transpose(0, 1).unsqueeze(0)
@@ -265,7 +280,7 @@ class _OutProj(torch.autograd.Function):
 
 
 class HyenaOperator(nn.Module):
-    """Hyena operator (hyena.py:270-448), order-2 hot path on sm_100a.
+    """Hyena operator (hyena.py:270-448): order 2 as one fused pass on sm_100a, order >= 3 as a chain of its kernels.
 
     forward(u: (B, L, D)) -> (B, L, D) (or ``(y, None)`` when return_state).  Unknown keyword arguments
     (layer_idx, device, dtype, ...) fall through to the filter exactly as in the reference."""
@@ -275,7 +290,7 @@ class HyenaOperator(nn.Module):
                  post_order_ffn=False, jit_filter=False, short_filter_order=3, activation="id", return_state=False,
                  **filter_args):
         super().__init__()
-        unsupported = {"order": order != 2, "num_heads": num_heads != 1, "inner_factor": inner_factor != 1,
+        unsupported = {"order": order < 2, "num_heads": num_heads != 1, "inner_factor": inner_factor != 1,
                        "num_blocks": num_blocks != 1, "outer_mixing": outer_mixing, "dropout": dropout != 0.0,
                        "filter_dropout": filter_dropout != 0.0, "post_order_ffn": post_order_ffn,
                        "jit_filter": jit_filter, "short_filter_order": short_filter_order != 3,
@@ -308,21 +323,54 @@ class HyenaOperator(nn.Module):
         u = u.to(torch.float32)
         l = u.size(-2)
         l_filter = min(l, self.l_max)
-        k = self.filter_fn.filter_channel_major(l_filter)                           # (D, l_filter)
+        k = self.filter_fn.filter_channel_major(l_filter)                           # (D*(order-1), l_filter)
         fb = self.filter_fn.bias if self.filter_fn.use_bias else 0 * self.filter_fn.bias
-        if ops.proj_mode() == "tc" and l_filter == l and ops.fuse_fir():
+        kspec = None
+        if self.order == 2 and getattr(self.filter_fn, "cache_filter", False):
+            # spectrum of the cached filter, kept with it (same invalidation: it is keyed on the cached k tensor)
+            c = getattr(self, "_kspec_cache", None)
+            kkey = (k.data_ptr(), k._version, tuple(k.shape))
+            if c is not None and c[0] == kkey:
+                kspec = c[1]
+            else:
+                kspec = ops.filter_spectrum(k.detach())
+                self._kspec_cache = (kkey, kspec)
+        if self.order > 2:
+            y_pre = self._forward_chained(u, k, fb, l_filter)
+        elif ops.proj_mode() == "tc" and l_filter == l and ops.fuse_fir():
             # one autograd node: in_proj GEMM + fused core; backward feeds ds straight into the projection GEMMs
             y_pre = ops.HyenaInCoreFn.apply(u, self.in_proj.weight, self.in_proj.bias, self.short_filter.weight,
-                                            self.short_filter.bias, k, fb)
+                                            self.short_filter.bias, k, fb, kspec)
         else:
             p = _InProj.apply(u, self.in_proj.weight)                               # (B, 3D, l)
             if l_filter < l:
                 p = p[..., :l_filter].contiguous()
-            y_pre = ops.HyenaCoreFn.apply(p, self.in_proj.bias, self.short_filter.weight, self.short_filter.bias, k, fb)
+            y_pre = ops.HyenaCoreFn.apply(p, self.in_proj.bias, self.short_filter.weight, self.short_filter.bias, k, fb,
+                                          kspec)
         y = _OutProj.apply(y_pre, self.out_proj.weight, self.out_proj.bias).to(in_dtype)
         if self.return_state:
             return y, None
         return y
+
+    def _forward_chained(self, u, k, fb, l_filter):
+        """order >= 3 (the shipped HyenaDNA layer default is 3, configs/model/layer/hyena_dna.yaml:3): the recurrence of
+        hyena.py:414-423 as a chain of this library's long convolutions.  Projections and every FFT convolution
+        (forward and backward) run on the sm_100a kernels; the gates and the 3-tap short filter between them are
+        plain elementwise / depthwise torch ops here -- the fully fused pass exists for order 2 only."""
+        D, O1 = self.d_model, self.order - 1
+        from .fftconv import fftconv_func
+        p = _InProj.apply(u, self.in_proj.weight)                                   # (B, (order+1) D, l)
+        if l_filter < p.shape[-1]:
+            p = p[..., :l_filter]
+        p = p + self.in_proj.bias[None, :, None]
+        uc = torch.nn.functional.conv1d(p, self.short_filter.weight, self.short_filter.bias,
+                                        padding=self.short_filter_order - 1, groups=p.shape[1])[..., :l_filter]
+        *x, v = uc.split(D, dim=1)
+        kk = k.reshape(D, O1, l_filter)                                             # filter channels are ordered (v o): :408-412
+        bb = fb.reshape(D, O1)
+        for o, x_i in enumerate(reversed(x[1:])):
+            v = fftconv_func((v * x_i).contiguous(), kk[:, o].contiguous(), bb[:, o].contiguous(), gelu=False)
+        return (v * x[0]).contiguous()
 
     @property
     def d_output(self):

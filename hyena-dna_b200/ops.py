@@ -133,9 +133,11 @@ class HyenaFilterFn(torch.autograd.Function):
     """Differentiable implicit filter: parameters -> k (D, L)."""
 
     @staticmethod
-    def forward(ctx, z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, shift, modulate, L):
+    def forward(ctx, z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, shift, modulate, L, cached=None):
         ctx.save_for_backward(z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas)
         ctx.cfg = (shift, modulate, L)
+        if cached is not None:                 # same inputs as the call that produced it (HyenaFilter.filter_channel_major)
+            return cached.detach()
         return filter_forward(z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, shift, modulate, L)
 
     @staticmethod
@@ -151,7 +153,7 @@ class HyenaFilterFn(torch.autograd.Function):
         if need_dz:
             gz = torch.zeros_like(z)
             (gz[0, :L] if z.dim() == 3 else gz[:L]).copy_(dz)
-        return (gz, None, *grads, dfreq.reshape(freq.shape), None, None, None, None)
+        return (gz, None, *grads, dfreq.reshape(freq.shape), None, None, None, None, None)
 
 
 # ------------------------------------------------------------------------------------------ spectrum / core
@@ -279,12 +281,13 @@ class HyenaCoreFn(torch.autograd.Function):
     """(p, in_bias, short filter, k, filter bias) -> y_pre (B, D, L); hyena.py:394-432 for order 2."""
 
     @staticmethod
-    def forward(ctx, p, in_bias, sw, sb, k, fbias):
+    def forward(ctx, p, in_bias, sw, sb, k, fbias, kspec=None):
         p = p.contiguous()
         sw2 = sw.reshape(sw.shape[0], -1).contiguous()
         sb = sb.contiguous(); fbias = fbias.contiguous()
         ib = in_bias.contiguous() if in_bias is not None else None
-        kspec = filter_spectrum(k)
+        if kspec is None:
+            kspec = filter_spectrum(k)
         need = any(ctx.needs_input_grad)
         y, c, gs = core_forward(p, ib, sw2, sb, kspec, fbias, need)
         ctx.save_for_backward(p, ib, sw2, sb, kspec, fbias, c, gs)
@@ -295,7 +298,7 @@ class HyenaCoreFn(torch.autograd.Function):
     def backward(ctx, dy):
         p, ib, sw2, sb, kspec, fbias, c, gs = ctx.saved_tensors
         dp, dk, dsw, dsb, dfb, dib = core_backward(dy, p, ib, sw2, sb, kspec, fbias, c, gs)
-        return dp, dib, dsw.reshape(ctx.sw_shape), dsb, dk, dfb
+        return dp, dib, dsw.reshape(ctx.sw_shape), dsb, dk, dfb, None
 
 
 class HyenaInCoreFn(torch.autograd.Function):
@@ -306,13 +309,14 @@ class HyenaInCoreFn(torch.autograd.Function):
     neither dp nor a separate short-filter backward pass exists (hyena.py:391-432 and its autograd)."""
 
     @staticmethod
-    def forward(ctx, u, W, in_bias, sw, sb, k, fbias):
+    def forward(ctx, u, W, in_bias, sw, sb, k, fbias, kspec=None):
         u = u.contiguous(); W = W.contiguous()
         sw2 = sw.reshape(sw.shape[0], -1).contiguous()
         sb = sb.contiguous(); fbias = fbias.contiguous()
         ib = in_bias.contiguous() if in_bias is not None else None
         p = proj_gemm(u, 0, W, False, 0)
-        kspec = filter_spectrum(k)
+        if kspec is None:
+            kspec = filter_spectrum(k)
         need = any(ctx.needs_input_grad)
         y, c, gs = core_forward(p, ib, sw2, sb, kspec, fbias, need)
         ctx.save_for_backward(u, W, p, ib, sw2, sb, kspec, fbias, c, gs)
@@ -325,7 +329,7 @@ class HyenaInCoreFn(torch.autograd.Function):
         ds, dk, dsw, dsb, dfb, dib = core_backward(dy, p, ib, sw2, sb, kspec, fbias, c, gs, return_ds=True)
         du = proj_gemm(ds, 1, W, True, 1, fir=sw2) if ctx.needs_input_grad[0] else None
         dW = proj_wgrad(ds, u, fir=sw2) if ctx.needs_input_grad[1] else None
-        return du, dW, dib, dsw.reshape(ctx.sw_shape), dsb, dk, dfb
+        return du, dW, dib, dsw.reshape(ctx.sw_shape), dsb, dk, dfb, None
 
 
 # ------------------------------------------------------------------------------------------ plain fftconv

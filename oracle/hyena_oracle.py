@@ -50,7 +50,7 @@ def init_params(d_model, l_max, order=2, filter_order=64, emb_dim=3, w=1.0, shor
     ``_init_weights`` (standalone_hyenadna.py:612-641): Linear weights N(0, std), biases 0,
     out_proj.weight N(0, std/sqrt(2 n_layer)).
     """
-    assert order == 2
+    assert order >= 2
     D, N, E = d_model, filter_order, emb_dim
     g = generator
 
@@ -65,22 +65,22 @@ def init_params(d_model, l_max, order=2, filter_order=64, emb_dim=3, w=1.0, shor
         return W, b
 
     P = {}
-    P["in_proj.weight"], P["in_proj.bias"] = lin(3 * D, D)
+    P["in_proj.weight"], P["in_proj.bias"] = lin((order + 1) * D, D)
     P["out_proj.weight"], P["out_proj.bias"] = lin(D, D)
     if init_std is not None:
         P["out_proj.weight"] = torch.randn(D, D, generator=g) * init_std / math.sqrt(2 * n_layer)
     bound = 1.0 / math.sqrt(short_filter_order)
-    P["short_filter.weight"] = (torch.rand(3 * D, 1, short_filter_order, generator=g) * 2 - 1) * bound
-    P["short_filter.bias"] = (torch.rand(3 * D, generator=g) * 2 - 1) * bound
-    P["filter_fn.bias"] = torch.randn(D, generator=g)
+    P["short_filter.weight"] = (torch.rand((order + 1) * D, 1, short_filter_order, generator=g) * 2 - 1) * bound
+    P["short_filter.bias"] = (torch.rand((order + 1) * D, generator=g) * 2 - 1) * bound
+    P["filter_fn.bias"] = torch.randn(D * (order - 1), generator=g)
     z, t = positional_embedding(E, l_max)
     P["filter_fn.pos_emb.z"], P["filter_fn.pos_emb.t"] = z, t
     P["filter_fn.implicit_filter.0.weight"], P["filter_fn.implicit_filter.0.bias"] = lin(N, E)
     P["filter_fn.implicit_filter.2.weight"], P["filter_fn.implicit_filter.2.bias"] = lin(N, N)
     P["filter_fn.implicit_filter.4.weight"], P["filter_fn.implicit_filter.4.bias"] = lin(N, N)
-    P["filter_fn.implicit_filter.6.weight"], _ = lin(D, N, bias=False)
+    P["filter_fn.implicit_filter.6.weight"], _ = lin(D * (order - 1), N, bias=False)
     P["filter_fn.implicit_filter.1.freq"] = w * torch.ones(1, N)
-    P["filter_fn.modulation.deltas"] = modulation_deltas(D)
+    P["filter_fn.modulation.deltas"] = modulation_deltas(D * (order - 1))
     return {k: v.to(dtype) for k, v in P.items()}
 
 
@@ -151,21 +151,26 @@ def short_filter(p, W, b, L):
 
 
 def hyena_operator(u, P, shift=0.0, modulate=True, return_intermediates=False):
-    """HyenaOperator.forward for order=2, heads=1, blocks=1, activation=id, dropout=0.
+    """HyenaOperator.forward for any order >= 2 (heads=1, blocks=1, activation=id, dropout=0); the order is read off
+    in_proj.weight ((order+1)*D rows).
 
-    src/models/sequence/hyena.py:388-444 (== standalone_hyenadna.py:273-293).
-    u (B, L, D) -> (B, L, D)."""
+    src/models/sequence/hyena.py:388-444 (== standalone_hyenadna.py:273-293).  u (B, L, D) -> (B, L, D)."""
     B, L, D = u.shape
+    order = P["in_proj.weight"].shape[0] // D - 1
     p = F.linear(u, P["in_proj.weight"], P["in_proj.bias"]).transpose(1, 2)       # :391-392
     uc = short_filter(p, P["short_filter.weight"], P["short_filter.bias"], L)      # :394
-    x0, x1, v = uc.split(D, dim=1)                                                 # :404
-    k = hyena_filter(L, P, shift, modulate)[0].transpose(0, 1)                      # :405-408  (D, L)
-    g = v * x1                                                                     # :420
-    c = fftconv_ref(g, k, P["filter_fn.bias"])                                     # :423
-    y_pre = (c * x0).transpose(1, 2)                                               # :432-439
+    *x, v = uc.split(D, dim=1)                                                     # :404
+    # filter channels are ordered (v o): channel = v * (order-1) + o                 :405-412
+    k = hyena_filter(L, P, shift, modulate)[0].transpose(0, 1).reshape(D, order - 1, L)
+    bias = P["filter_fn.bias"].reshape(D, order - 1)
+    g = c = None
+    for o, x_i in enumerate(reversed(x[1:])):                                      # :414-423
+        g = v * x_i                                                                # :420
+        v = c = fftconv_ref(g, k[:, o], bias[:, o])                                # :423
+    y_pre = (v * x[0]).transpose(1, 2)                                             # :432-439
     y = F.linear(y_pre, P["out_proj.weight"], P["out_proj.bias"])                  # :440
     if return_intermediates:
-        return y, dict(p=p, uc=uc, k=k, g=g, c=c, y_pre=y_pre)
+        return y, dict(p=p, uc=uc, k=k[:, -1], g=g, c=c, y_pre=y_pre)
     return y
 
 

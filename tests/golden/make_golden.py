@@ -26,6 +26,9 @@ CASES = {
     "ref_L256_D16":   (2, 256, 16, 5, 10.0, 256, 0.02),
     "ref_L250_lmax300_D8": (1, 250, 8, 5, 10.0, 300, None),   # L < l_max, L not a power of two
     "tiny_1k":        (2, 1024, 128, 5, 10.0, 1024, 0.02),   # BASELINE.json configs[0]
+    # order = 3: the shipped HyenaDNA layer default (configs/model/layer/hyena_dna.yaml:3), two chained recurrences
+    "ref_order3_L256_D16": (2, 256, 16, 5, 10.0, 256, 0.02, 3),
+    "ref_order3_L200_D8":  (1, 200, 8, 5, 10.0, 256, None, 3),
 }
 
 
@@ -47,15 +50,16 @@ def _shim():
 
 
 def build(case, which):
-    B, L, D, E, w, l_max, init_std = CASES[case]
+    B, L, D, E, w, l_max, init_std = CASES[case][:7]
+    order = CASES[case][7] if len(CASES[case]) > 7 else 2
     torch.manual_seed(1234)
     if which == "standalone":
         import standalone_hyenadna as S
-        op = S.HyenaOperator(D, l_max, order=2, filter_order=64, emb_dim=E, w=w, shift=0.0, lr_pos_emb=0.0)
+        op = S.HyenaOperator(D, l_max, order=order, filter_order=64, emb_dim=E, w=w, shift=0.0, lr_pos_emb=0.0)
         init = S._init_weights
     else:
         from src.models.sequence.hyena import HyenaOperator
-        op = HyenaOperator(D, l_max, order=2, filter_order=64, emb_dim=E, w=w, lr_pos_emb=0.0,
+        op = HyenaOperator(D, l_max, order=order, filter_order=64, emb_dim=E, w=w, lr_pos_emb=0.0,
                            layer_idx=0, device=None, dtype=None)
         import standalone_hyenadna as S
         init = S._init_weights
@@ -70,18 +74,29 @@ def main():
     torch.set_num_threads(8)
     sys.path.insert(0, REF)
     _shim()
-    for case, (B, L, D, E, w, l_max, init_std) in CASES.items():
+    only = sys.argv[1:]
+    for case, spec in CASES.items():
+        if only and case not in only:
+            continue
+        B, L, D, E, w, l_max, init_std = spec[:7]
+        order = spec[7] if len(spec) > 7 else 2
         op = build(case, "standalone")
         op_src = build(case, "src")
         op_src.load_state_dict(op.state_dict())
+        if order > 2:
+            # the two copies of the operator in the reference disagree beyond order 2: standalone_hyenadna.py:283-284
+            # orders the filter channels '(o d)', src/models/sequence/hyena.py:408-412 '(v o)'.  The drop-in target is
+            # the src module, so the fixture comes from it.
+            op, op_src = op_src, None
         g = torch.Generator().manual_seed(0)
         u = torch.randn(B, L, D, generator=g)
         dy = torch.randn(B, L, D, generator=torch.Generator().manual_seed(1))
         u1 = u.clone().requires_grad_(True)
         y = op(u1)
         y.backward(dy)
-        y_src = op_src(u)
-        assert torch.equal(y, y_src), "standalone and src/ HyenaOperator disagree"
+        if op_src is not None:
+            y_src = op_src(u)
+            assert torch.equal(y, y_src), "standalone and src/ HyenaOperator disagree"
         op64 = copy.deepcopy(op).double()
         op64.zero_grad()
         u64 = u.double().requires_grad_(True)
@@ -89,7 +104,7 @@ def main():
         y64.backward(dy.double())
         out = {"u": u.numpy(), "dy": dy.numpy(), "y": y.detach().numpy(), "du": u1.grad.numpy(),
                "y64": y64.detach().numpy(), "du64": u64.grad.numpy(),
-               "meta": np.array([B, L, D, E, l_max], dtype=np.int64), "w": np.float64(w)}
+               "meta": np.array([B, L, D, E, l_max], dtype=np.int64), "w": np.float64(w), "order": np.int64(order)}
         for k, v in op.state_dict().items():
             out["sd/" + k] = v.numpy()
         for k, p in op.named_parameters():

@@ -5,7 +5,8 @@ import numpy as np
 import torch
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = ["ref_L64_D8", "ref_L256_D16", "ref_L250_lmax300_D8", "tiny_1k"]
+CASES = ["ref_L64_D8", "ref_L256_D16", "ref_L250_lmax300_D8", "tiny_1k"]      # order = 2
+CASES_ORDER3 = ["ref_order3_L256_D16", "ref_order3_L200_D8"]
 
 
 def load(case):

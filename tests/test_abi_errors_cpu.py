@@ -55,7 +55,7 @@ def test_workspace_sizing_is_consistent():
 
 def test_module_rejects_options_outside_the_hot_path():
     import hyena_dna_b200 as H
-    for kw in (dict(order=3), dict(num_heads=2), dict(dropout=0.1), dict(activation="gelu"), dict(outer_mixing=True),
+    for kw in (dict(order=1), dict(num_heads=2), dict(dropout=0.1), dict(activation="gelu"), dict(outer_mixing=True),
                dict(bidirectional=True), dict(filter_order=16), dict(short_filter_order=4)):
         with pytest.raises(H.HyenaB200Error):
             H.HyenaOperator(8, 64, **kw)

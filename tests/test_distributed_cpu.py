@@ -45,6 +45,29 @@ def _worker(rank, world, port, out):
         # gather of batch shards restores the global batch order
         y = D.gather_outputs(x[rank * 2: rank * 2 + 2])
         assert torch.equal(y, x[:4])
+        # hook-driven two-bucket reducer: same sums as the flat all-reduce, both buckets, reusable across steps
+        lin1, lin2 = torch.nn.Linear(3, 4), torch.nn.Linear(4, 2)
+        with torch.no_grad():
+            for q in list(lin1.parameters()) + list(lin2.parameters()):
+                q.copy_(torch.arange(q.numel(), dtype=torch.float32).reshape(q.shape) * 0.01)
+        named = [("a.weight", lin1.weight), ("a.bias", lin1.bias), ("implicit_filter.w", lin2.weight),
+                 ("implicit_filter.b", lin2.bias)]
+        red = D.OverlappedGradReducer([q for _, q in named], named=named)
+        for step in range(2):
+            for _, q in named:
+                q.grad = None
+            xin = torch.full((2, 3), float(rank + 1 + step))
+            lin2(lin1(xin)).sum().backward()
+            local = [q.grad.clone() for _, q in named]
+            red.finish()
+            outs = [torch.zeros_like(g) for g in local]
+            for g, o in zip(local, outs):
+                gl = [torch.zeros_like(g) for _ in range(world)]
+                dist.all_gather(gl, g)
+                o.copy_(sum(gl))
+            for (_, q), o in zip(named, outs):
+                assert torch.allclose(q.grad, o, rtol=1e-6, atol=1e-6), "OverlappedGradReducer sum mismatch"
+        red.remove()
         out.put((rank, "ok"))
     except Exception as e:   # pragma: no cover
         out.put((rank, repr(e)))
@@ -105,4 +128,4 @@ def test_product_path_fails_loudly_without_gpu():
     with pytest.raises(H.HyenaB200Error):
         H.fftconv_func(torch.randn(1, 2, 64), torch.randn(2, 64), torch.randn(2), gelu=False)
     with pytest.raises(H.HyenaB200Error):
-        H.HyenaOperator(8, 64, order=3)
+        H.HyenaOperator(8, 64, num_heads=2)

@@ -515,3 +515,92 @@ def test_proj_wgrad_tcgen05_matches_fp64(B, L, M, N):
     ref_f = torch.einsum("bml,bln->mn", dp, Y.double())
     got_f = H.ops.proj_wgrad(X.to(dev), Y.to(dev), fir=taps.to(dev))
     _close(got_f, ref_f, f"wgrad fused FIR {B}x{L}x{M}x{N}")
+
+
+# ------------------------------------------------------------------------------------------ order 3
+@pytest.mark.parametrize("case", ["ref_order3_L256_D16", "ref_order3_L200_D8"])
+def test_operator_order3_matches_reference_golden(case):
+    """order = 3 (configs/model/layer/hyena_dna.yaml:3; recurrence loop hyena.py:414-423) against vectors generated by the
+    unmodified src/models/sequence/hyena.py (filter channels ordered '(v o)', hyena.py:408-412)."""
+    import hyena_dna_b200 as H
+    dev = _dev()
+    G = load(case)
+    op = H.HyenaOperator(G["D"], G["l_max"], order=3, filter_order=64, emb_dim=G["E"], w=G["w"], lr_pos_emb=0.0)
+    op.load_state_dict(G["sd"], strict=True)
+    op = op.to(dev)
+    u = G["u"].to(dev).requires_grad_(True)
+    y = op(u)
+    y.backward(G["dy"].to(dev))
+    _close(y, G["y"], f"{case} y")
+    _close(u.grad, G["du"], f"{case} du")
+    got = dict(op.named_parameters())
+    for name, gref in G["grad"].items():
+        _close(got[name].grad, gref, f"{case} grad {name}", rtol=2e-3, atol=2e-5)
+
+
+def test_operator_order3_long_sequence_matches_oracle_fp64():
+    dev = _dev()
+    import hyena_dna_b200 as H
+    B, L, D = 1, 65536, 16
+    g = torch.Generator().manual_seed(33)
+    P = O.init_params(D, L, order=3, emb_dim=5, w=10.0, generator=g, init_std=0.02)
+    u, _ = O.nucleotide_activations(B, L, D, seed=2222)
+    dy = torch.randn(B, L, D, generator=torch.Generator().manual_seed(1))
+    y64, du64, g64 = O.operator_fwd_bwd(u.double(), O.to_dtype(P, torch.float64), dy.double())
+    sd = dict(P)
+    for extra in ("filter_fn.implicit_filter.3.freq", "filter_fn.implicit_filter.5.freq"):
+        sd[extra] = sd["filter_fn.implicit_filter.1.freq"]
+    op = H.HyenaOperator(D, L, order=3, filter_order=64, emb_dim=5, w=10.0, lr_pos_emb=0.0)
+    op.load_state_dict(sd, strict=True)
+    op = op.to(dev)
+    ug = u.to(dev).requires_grad_(True)
+    y = op(ug)
+    y.backward(dy.to(dev))
+    _close(y, y64, "order3 y")
+    _close(ug.grad, du64, "order3 du")
+    got = dict(op.named_parameters())
+    for name, gref in g64.items():
+        _close(got[name].grad, gref, f"order3 grad {name}", rtol=2e-3, atol=2e-5)
+
+
+# ------------------------------------------------------------------------------------------ checkpointed stack (f2)
+def test_checkpointed_stack_reuses_filter_and_matches_plain_autograd():
+    """Two operators with a residual connection, each in its own checkpoint region: same outputs and gradients as the plain
+    stack, and the recompute forward launches NO filter / spectrum kernels (cache hit), cf. long_conv_lm.py:39-45."""
+    import hyena_dna_b200 as H
+    dev = _dev()
+    torch.manual_seed(3)
+    B, L, D = 1, 4096, 32
+    layers = [H.HyenaOperator(D, L, emb_dim=5, w=10.0, lr_pos_emb=0.0) for _ in range(2)]
+    plain = H.CheckpointedHyenaStack(layers, use_checkpoint=False, cache_filter=False).to(dev)
+    u = torch.randn(B, L, D, device=dev)
+    dy = torch.randn(B, L, D, device=dev)
+    up = u.clone().requires_grad_(True)
+    yp = plain(up)
+    yp.backward(dy)
+    ref = {n: p.grad.clone() for n, p in plain.named_parameters()}
+    for p in plain.parameters():
+        p.grad = None
+    ck = H.CheckpointedHyenaStack(layers, use_checkpoint=True, cache_filter=True).to(dev)
+    uc = u.clone().requires_grad_(True)
+    yc = ck(uc)
+    H._lib.profile_begin()
+    yc.backward(dy)
+    prof = H._lib.profile_end()
+    _close(yc, yp, "checkpointed y")
+    _close(uc.grad, up.grad, "checkpointed du")
+    for n, p in ck.named_parameters():
+        _close(p.grad, ref[n], f"checkpointed grad {n}", rtol=2e-3, atol=2e-5)
+    # the backward window contains the recompute forwards: no forward filter / filter-spectrum kernels in it
+    assert "filter_tc_fwd" not in prof and "row_pass<filter>" not in prof and "col_fwd<filter>" not in prof, prof.keys()
+    # an optimizer step invalidates the cache
+    with torch.no_grad():
+        for p in ck.parameters():
+            p.add_(0.01 * torch.randn_like(p))
+    H._lib.profile_begin()
+    with torch.no_grad():
+        ck(u)
+    prof2 = H._lib.profile_end()
+    assert "filter_tc_fwd" in prof2
+    plan = H.memory_plan(1, 1 << 20, 256, 8)
+    assert plan["total"] < 180e9

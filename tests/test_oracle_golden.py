@@ -3,10 +3,10 @@ import pytest
 import torch
 
 from oracle import hyena_oracle as O
-from tests.golden_util import CASES, load
+from tests.golden_util import CASES, CASES_ORDER3, load
 
 
-@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("case", CASES + CASES_ORDER3)
 def test_oracle_forward_backward_matches_reference(case):
     G = load(case)
     P = O.canonical(G["sd"])
@@ -20,7 +20,7 @@ def test_oracle_forward_backward_matches_reference(case):
         assert float((grads[kk] - g).abs().max()) <= 2e-5 * scale + 1e-7, k
 
 
-@pytest.mark.parametrize("case", ["ref_L64_D8", "ref_L256_D16", "ref_L250_lmax300_D8"])
+@pytest.mark.parametrize("case", ["ref_L64_D8", "ref_L256_D16", "ref_L250_lmax300_D8"] + CASES_ORDER3)
 def test_oracle_fp64_matches_reference_fp64(case):
     G = load(case)
     P = O.to_dtype(O.canonical(G["sd"]), torch.float64)
