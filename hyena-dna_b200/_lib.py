@@ -46,6 +46,7 @@ SIGNATURES = {
     "hyena_b200_fftconv_bwd": (_i, [c_fp] * 7 + [_i, _i, _i, _vp, _sz, _vp]),
     "hyena_b200_gemm_available": (_i, []),
     "hyena_b200_proj_wimg_bytes": (_sz, [_i, _i]),
+    "hyena_b200_proj_debug_buffer": (_i, [_vp]),
     "hyena_b200_proj_wgrad_scratch_bytes": (_sz, [_i, _i]),
     "hyena_b200_proj_wgrad": (_i, [c_fp, c_fp, c_fp, c_fp, _i, _f, _i, _i, _i, _i, _vp, _sz, _vp]),
     "hyena_b200_proj_gemm": (_i, [c_fp, _i, c_fp, _i, _i, c_fp, c_fp, c_fp, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),

@@ -12,6 +12,7 @@
 
 namespace hy {
 
+extern long long* g_proj_dbg;          // k_proj.cu
 static thread_local char g_err[512] = "";
 static std::atomic<unsigned long long> g_launches{0};
 
@@ -517,6 +518,9 @@ HY_API int hyena_b200_proj_gemm(const float* act, int act_layout, const float* W
                            reinterpret_cast<float*>(wimg), (cudaStream_t)stream));
   return 0;
 }
+
+/* debug: device buffer of >= 16 long longs receiving the per-role barrier-wait cycle counters of CTA 0 (NULL: off) */
+HY_API int hyena_b200_proj_debug_buffer(void* buf) { hy::g_proj_dbg = reinterpret_cast<long long*>(buf); return 0; }
 
 HY_API size_t hyena_b200_proj_wgrad_scratch_bytes(int M, int N) { return (M < 1 || N < 1) ? 0 : proj_wgrad_scratch_bytes(M, N); }
 

@@ -4,8 +4,10 @@
 
 namespace hy {
 
+long long* g_proj_dbg = nullptr;      // tools/dbg_proj_timing.py: device buffer for the per-role wait counters (debug)
+
 size_t proj_wimg_bytes(int N, int K) {
-  const int NT = (N % 192 == 0) ? 192 : 128;
+  const int NT = 128;
   return pg::wimg_floats(N, K, NT) * sizeof(float);
 }
 
@@ -36,7 +38,7 @@ static cudaError_t by_layout(const pg::Args& a, int act_layout, int out_layout, 
 cudaError_t launch_proj_gemm(const float* act, int act_layout, const float* W, int ldw, int w_transposed, const float* bias,
                              const float* fir, float* out, int out_layout, int B, int L, int K, int N, int l0, int ln,
                              float* wimg, cudaStream_t s) {
-  const int NT = (N % 192 == 0) ? 192 : 128;
+  const int NT = 128;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -50,13 +52,14 @@ cudaError_t launch_proj_gemm(const float* act, int act_layout, const float* W, i
   if (e != cudaSuccess) return e;
   pg::Args a;
   a.act = act; a.wimg = wimg; a.out = out; a.bias = bias; a.fir = fir;
+  a.dbg = g_proj_dbg;
   a.B = B; a.L = L; a.K = K; a.N = N; a.l0 = l0; a.ln = ln;
   if (act_layout == pg::ACT_ROW) a.vec = (K % 4 == 0);
   else a.vec = (L % 4 == 0) && (l0 % 4 == 0) && (ln % 4 == 0);
   a.kchunks = (K + pg::kKC - 1) / pg::kKC;
   a.ntiles_n = (N + NT - 1) / NT;
   a.mtiles_per_b = (ln + 127) / 128;
-  return NT == 192 ? by_layout<192>(a, act_layout, out_layout, sms, s) : by_layout<128>(a, act_layout, out_layout, sms, s);
+  return by_layout<128>(a, act_layout, out_layout, sms, s);
 }
 
 

@@ -14,7 +14,11 @@
 //   B operand the weights, pre-split once per call into hi / lo images in the canonical no-swizzle K-major
 //             core-matrix layout (proj_prep_kernel), streamed by TMA bulk copies (cp.async.bulk, SASS UBLKCP) into a
 //             ring of shared-memory stages guarded by mbarriers
-//   D         fp32 accumulators in TMEM, double buffered: the epilogue of tile i overlaps the MMAs of tile i+1
+//   D         fp32 accumulators in TMEM, two buffers used in turn for every PAIR of K chunks (24 MMAs); the epilogue
+//             warps drain each pair into per-thread fp32 registers (round-to-nearest adds) while the next pair is being
+//             multiplied.  Reason: the tensor core adds into its accumulator with truncation, so a long chain biases the
+//             result by ~(number of MMAs) x 2^-24 towards zero -- measured here: 96 chained MMAs (K = 256) cost 4x the
+//             error of cuBLASLt's BF16x9 on y at L = 2^20, the 2^20-position weight gradients lost four digits.
 //   3xTF32    x = hi + lo, hi = rna_tf32(x), lo = rna_tf32(x - hi);  D += Ahi Bhi + Alo Bhi + Ahi Blo   (lo*lo < 2^-22)
 //
 // Warp roles (320 threads): warps 0-3 stage + convert (thread = position), warps 4-7 epilogue (thread = position),
@@ -58,6 +62,7 @@ struct Args {
   int ntiles_n;          // ceil(N / NT)
   int mtiles_per_b;      // ceil(ln / 128)
   int vec;               // 1: 16-byte cp.async staging is legal (alignment / divisibility checked on the host)
+  long long* dbg;        // optional (tools/dbg_proj_timing.py): per-role wait / work cycle counters of CTA 0, or null
 };
 
 // ------------------------------------------------------------------------------------------------ weight images
@@ -88,7 +93,7 @@ __host__ __device__ constexpr size_t wimg_floats(int N, int K, int NT) {
 
 // ------------------------------------------------------------------------------------------------ the kernel
 template <int NT> struct Cfg {
-  static constexpr int STAGES = NT >= 192 ? 2 : 3;                     // weight stages (the weights come from L2)
+  static constexpr int STAGES = 4;                                     // weight stages (the weights come from L2)
   static constexpr uint32_t STAGE_BYTES = 2u * NT * kKC * 4u;          // hi + lo image of one K chunk
   static constexpr uint32_t D_COLS = NT;                               // per accumulator buffer
   static constexpr uint32_t A_COL0 = 2 * NT;                           // A buffers after the two accumulators
@@ -98,7 +103,7 @@ template <int NT> struct Cfg {
   static constexpr size_t OFF_FIR = OFF_BAR + 256;
   static constexpr size_t SMEM = OFF_FIR;                              // + 12 K bytes of taps when the FIR is fused
   static_assert(2 * NT + 128 <= 512, "two accumulators and two A (hi, lo) chunk buffers must fit tensor memory");
-  static_assert(NT % 16 == 0 && NT >= 16 && NT <= 256, "UMMA N");
+  static_assert(NT == 128, "the epilogue keeps NT partial sums per thread in registers");
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -143,6 +148,20 @@ __global__ void __launch_bounds__(kThreads, 1) proj_gemm_kernel(const Args a) {
   tc::fence_after_sync();
   const uint32_t tmem = *tmem_p;
 
+  // debug timing: cycles spent in a barrier wait, accumulated per role (lane 0 of each role's first warp, CTA 0)
+  const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0;
+  long long dbg_t[6] = {0, 0, 0, 0, 0, 0};
+  auto timed_wait = [&](uint32_t bar, uint32_t parity, int slot) {
+    if (dbg_on) {
+      const long long t0 = clock64();
+      tc::mbar_wait_u(bar, parity);
+      dbg_t[slot] += clock64() - t0;
+    } else {
+      tc::mbar_wait_u(bar, parity);
+    }
+  };
+  const long long dbg_start = clock64();
+
   const int mtiles = a.B * a.mtiles_per_b;
   const long long ntiles = (long long)mtiles * a.ntiles_n;
   const int my_tiles = (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);      // tiles of this CTA (>= 1)
@@ -154,74 +173,111 @@ __global__ void __launch_bounds__(kThreads, 1) proj_gemm_kernel(const Args a) {
     const uint32_t lane_addr = tmem + ((uint32_t)(32 * warp) << 16);
     unsigned char* ring = smem + C::OFF_A;
 
-    // chunk index q of this CTA -> (batch, first position of the tile, first k)
-    auto locate = [&](long long q, int& b, int& lt, int& k0) {
-      const long long tile = blockIdx.x + (q / a.kchunks) * gridDim.x;
-      const int mt = (int)(tile / a.ntiles_n);
-      b = mt / a.mtiles_per_b;
-      lt = a.l0 + (mt - b * a.mtiles_per_b) * 128;
-      k0 = (int)(q % a.kchunks) * kKC;
+    // Cursors over this CTA's (tile, chunk) list, advanced incrementally (no divisions in the loop): one for the chunk
+    // being staged (kAStages - 1 ahead), one for the chunk being converted.
+    struct Cur { int tile, kc, b, lt; };
+    auto cur_set = [&](Cur& c, int tile) {
+      c.tile = tile; c.kc = 0;
+      const int mt = tile / a.ntiles_n;
+      c.b = mt / a.mtiles_per_b;
+      c.lt = a.l0 + (mt - c.b * a.mtiles_per_b) * 128;
     };
-    // fill staging slot q % kAStages with chunk q (asynchronously when the layout allows 16-byte copies)
-    auto stage = [&](long long q) {
-      int b, lt, k0;
-      locate(q, b, lt, k0);
-      unsigned char* st = ring + (size_t)(q % kAStages) * kAStageBytes;
-      const int lend = a.l0 + a.ln;
+    auto cur_next = [&](Cur& c) {
+      if (++c.kc == a.kchunks) cur_set(c, c.tile + (int)gridDim.x);
+    };
+    const int lend = a.l0 + a.ln;
+    // per-thread constants of the staging pattern
+    //   ACT_ROW: pieces (row (tid >> 3) + 16 i, 16-byte column tid & 7), i < 8: a warp copies four whole 128-byte rows
+    //   ACT_CH : pieces (channel (tid >> 5) + 4 i, quad tid & 31), i < 8: a warp copies 512 contiguous bytes of one channel
+    const int r0 = tid >> 3, c8 = tid & 7;
+    const int j0 = tid >> 5, q32 = tid & 31;
+    const uint32_t dst_row0 = (uint32_t)(r0 * 128 + ((c8 ^ (r0 & 7)) << 4));
+    const uint32_t dst_ch0 = (uint32_t)(j0 * kAPitchCh + q32 * 16);
+
+    // fill staging slot `slot` with the chunk at cursor c (asynchronously when the layout allows 16-byte copies)
+    auto stage = [&](const Cur& c, int slot) {
+      unsigned char* st = ring + (size_t)slot * kAStageBytes;
+      const int k0 = c.kc * kKC;
       if constexpr (ACT == ACT_ROW) {
-        // own row: 8 pieces of 16 B, swizzled by the row so that the read-back (same offsets, 128-byte row pitch) is
-        // bank-conflict free; thread-private, so no barrier between fill and use
-        const int l = lt + row;
-        const float* src = a.act + ((size_t)b * a.L + (l < lend ? l : 0)) * a.K + k0;
+        const float* base = a.act + ((size_t)c.b * a.L + c.lt) * a.K + k0;
         if (a.vec && k0 + kKC <= a.K) {
+          if (c.lt + 128 <= lend) {                                 // interior tile: no predicates
+            const float* src = base + (size_t)r0 * a.K + 4 * c8;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) cp_async16(st + row * 128 + ((c ^ (row & 7)) << 4), src + 4 * c, l < lend);
+            for (int i = 0; i < 8; ++i) cp_async16(st + dst_row0 + i * 2048, src + (size_t)i * 16 * a.K, true);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const bool ok = c.lt + r0 + 16 * i < lend;
+              cp_async16(st + dst_row0 + i * 2048, base + (ok ? (size_t)(r0 + 16 * i) * a.K + 4 * c8 : 0), ok);
+            }
+          }
         } else {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
+          for (int i = 0; i < 8; ++i) {
+            const int r = r0 + 16 * i;
+            const bool rv = c.lt + r < lend;
+            const float* src = base + (size_t)(rv ? r : 0) * a.K + 4 * c8;
             float4 v;
-            v.x = (l < lend && k0 + 4 * c + 0 < a.K) ? __ldg(src + 4 * c + 0) : 0.f;
-            v.y = (l < lend && k0 + 4 * c + 1 < a.K) ? __ldg(src + 4 * c + 1) : 0.f;
-            v.z = (l < lend && k0 + 4 * c + 2 < a.K) ? __ldg(src + 4 * c + 2) : 0.f;
-            v.w = (l < lend && k0 + 4 * c + 3 < a.K) ? __ldg(src + 4 * c + 3) : 0.f;
-            *reinterpret_cast<float4*>(st + row * 128 + ((c ^ (row & 7)) << 4)) = v;
+            v.x = (rv && k0 + 4 * c8 + 0 < a.K) ? __ldg(src + 0) : 0.f;
+            v.y = (rv && k0 + 4 * c8 + 1 < a.K) ? __ldg(src + 1) : 0.f;
+            v.z = (rv && k0 + 4 * c8 + 2 < a.K) ? __ldg(src + 2) : 0.f;
+            v.w = (rv && k0 + 4 * c8 + 3 < a.K) ? __ldg(src + 3) : 0.f;
+            *reinterpret_cast<float4*>(st + dst_row0 + i * 2048) = v;
           }
         }
       } else {
-        // 32 channel rows of 128 (+4 look-ahead) positions; piece p = (channel p / 33, quad p % 33)
-        const int npieces = 32 * 33;
-        for (int p = tid; p < npieces; p += 128) {
-          const int j = p / 33, qd = p - j * 33;
-          if (qd == 32 && !use_fir) continue;
-          const int l = lt + 4 * qd;
-          // in-range test: the 128 tile positions stop at the processed range, the look-ahead quad at the tensor end
-          const int lim = (qd == 32) ? a.L : lend;
-          const bool kv = k0 + j < a.K;
-          const float* src = a.act + ((size_t)b * a.K + (kv ? k0 + j : 0)) * a.L;
-          unsigned char* dst = st + j * kAPitchCh + qd * 16;
-          if (a.vec) {
-            const bool ok = kv && (l + 4 <= lim);
-            cp_async16(dst, src + (ok ? l : 0), ok);
-          } else {
-            float4 v;
-            v.x = (kv && l + 0 < lim) ? __ldg(src + l + 0) : 0.f;
-            v.y = (kv && l + 1 < lim) ? __ldg(src + l + 1) : 0.f;
-            v.z = (kv && l + 2 < lim) ? __ldg(src + l + 2) : 0.f;
-            v.w = (kv && l + 3 < lim) ? __ldg(src + l + 3) : 0.f;
-            *reinterpret_cast<float4*>(dst) = v;
-          }
+        const float* base = a.act + ((size_t)c.b * a.K + k0) * a.L + c.lt;
+        const bool interior = (k0 + kKC <= a.K) && (c.lt + 128 <= lend) && (!use_fir || c.lt + 132 <= a.L);
+        if (a.vec && interior) {
+          const float* src = base + (size_t)j0 * a.L + 4 * q32;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) cp_async16(st + dst_ch0 + i * 4 * kAPitchCh, src + (size_t)i * 4 * a.L, true);
+          if (use_fir && tid < 32) cp_async16(st + tid * kAPitchCh + 512, base + (size_t)tid * a.L + 128, true);
+        } else {
+          // edge tile / ragged K / unaligned tensor: per-piece bounds; the 128 tile positions stop at the processed range,
+          // the look-ahead quad (fused FIR) at the end of the tensor
+          auto piece = [&](int j, int qd) {
+            const int l = c.lt + 4 * qd;
+            const int lim = (qd == 32) ? a.L : lend;
+            const bool kv = k0 + j < a.K;
+            const float* src = a.act + ((size_t)c.b * a.K + (kv ? k0 + j : 0)) * a.L;
+            unsigned char* dst = st + j * kAPitchCh + qd * 16;
+            if (a.vec) {
+              const bool ok = kv && (l + 4 <= lim);
+              cp_async16(dst, src + (ok ? l : 0), ok);
+            } else {
+              float4 v;
+              v.x = (kv && l + 0 < lim) ? __ldg(src + l + 0) : 0.f;
+              v.y = (kv && l + 1 < lim) ? __ldg(src + l + 1) : 0.f;
+              v.z = (kv && l + 2 < lim) ? __ldg(src + l + 2) : 0.f;
+              v.w = (kv && l + 3 < lim) ? __ldg(src + l + 3) : 0.f;
+              *reinterpret_cast<float4*>(dst) = v;
+            }
+          };
+#pragma unroll
+          for (int i = 0; i < 8; ++i) piece(j0 + 4 * i, q32);
+          if (use_fir && tid < 32) piece(tid, 32);
         }
       }
       cp_async_commit();
     };
 
-    for (int q = 0; q < kAStages - 1; ++q) {
-      if (q < nchunks) stage(q); else cp_async_commit();
+    Cur cs, cc;                                                     // staging cursor, conversion cursor
+    cur_set(cs, (int)blockIdx.x);
+    cc = cs;
+    int q_staged = 0;
+    for (; q_staged < kAStages - 1; ++q_staged) {
+      if (q_staged < nchunks) { stage(cs, q_staged % kAStages); cur_next(cs); } else cp_async_commit();
     }
-    for (long long q = 0; q < nchunks; ++q) {
+    for (int q = 0; q < (int)nchunks; ++q) {
+      long long tA = dbg_on ? clock64() : 0;
       cp_async_wait_group<kAStages - 2>();                         // chunk q has landed (this thread's pieces)
-      if constexpr (ACT == ACT_CH) named_bar_sync(1, 128);         // ... and everybody else's; slot (q-1) % S is free
-      if (q + kAStages - 1 < nchunks) stage(q + kAStages - 1); else cp_async_commit();
+      named_bar_sync(1, 128);                                      // ... and everybody else's; slot (q-1) % S is free
+      long long tB = dbg_on ? clock64() : 0;
+      if (q_staged < nchunks) { stage(cs, q_staged % kAStages); cur_next(cs); } else cp_async_commit();
+      ++q_staged;
+      long long tC = dbg_on ? clock64() : 0;
       const unsigned char* st = ring + (size_t)(q % kAStages) * kAStageBytes;
       float x[kKC];
       if constexpr (ACT == ACT_ROW) {
@@ -235,18 +291,20 @@ __global__ void __launch_bounds__(kThreads, 1) proj_gemm_kernel(const Args a) {
 #pragma unroll
           for (int j = 0; j < kKC; ++j) x[j] = *reinterpret_cast<const float*>(st + j * kAPitchCh + row * 4);
         } else {
-          int b, lt, k0;
-          locate(q, b, lt, k0);
           // dp[t] = w2 ds[t] + w1 ds[t+1] + w0 ds[t+2]; ds beyond the tensor end is zero (staged as zero), a position
-          // beyond the processed range produces a value nobody stores
+          // beyond the processed range produces a value nobody stores; taps of channels >= K are read as channel 0's and
+          // multiply staged zeros
+          const int k0 = cc.kc * kKC;
+          const bool kfull = k0 + kKC <= a.K;
 #pragma unroll
           for (int j = 0; j < kKC; ++j) {
-            const float* s = reinterpret_cast<const float*>(st + j * kAPitchCh) + row;
-            const int kk = (k0 + j < a.K) ? k0 + j : 0;
-            x[j] = fmaf(fir_s[3 * kk + 2], s[0], fmaf(fir_s[3 * kk + 1], s[1], fir_s[3 * kk] * s[2]));
+            const float* sp = reinterpret_cast<const float*>(st + j * kAPitchCh) + row;
+            const float* w = fir_s + 3 * ((kfull || k0 + j < a.K) ? k0 + j : 0);
+            x[j] = fmaf(w[2], sp[0], fmaf(w[1], sp[1], w[0] * sp[2]));
           }
         }
       }
+      cur_next(cc);
       uint32_t hi[kKC], lo[kKC];
 #pragma unroll
       for (int j = 0; j < kKC; ++j) {
@@ -256,70 +314,96 @@ __global__ void __launch_bounds__(kThreads, 1) proj_gemm_kernel(const Args a) {
       }
       const uint32_t it = (uint32_t)q;
       const int buf = it & 1;
-      tc::mbar_wait_u(A_EMPTY(buf), ((it >> 1) & 1) ^ 1);         // MMAs of the previous use of this buffer are done
+      long long tD = dbg_on ? clock64() : 0;
+      timed_wait(A_EMPTY(buf), ((it >> 1) & 1) ^ 1, 0);           // MMAs of the previous use of this buffer are done
       tc::fence_after_sync();
+      long long tE = dbg_on ? clock64() : 0;
       const uint32_t acol = C::A_COL0 + buf * 64;
       tc::tmem_st32(lane_addr + acol, hi);
       tc::tmem_st32(lane_addr + acol + 32, lo);
       tc::tmem_wait_st();
       tc::fence_before_sync();
       tc::mbar_arrive(A_FULL(buf));
+      if (dbg_on) { dbg_t[1] += tB - tA; dbg_t[2] += tC - tB; dbg_t[3] += tD - tC; dbg_t[4] += clock64() - tE; }
     }
     cp_async_wait_all();
+    if (dbg_on && tid == 0) { a.dbg[0] = dbg_t[0]; a.dbg[1] = clock64() - dbg_start; a.dbg[11] = dbg_t[1]; a.dbg[12] = dbg_t[2];
+                              a.dbg[13] = dbg_t[3]; a.dbg[14] = dbg_t[4]; }
   } else if (warp < 8) {
     // ================================================================== epilogue: thread = position of the tile
     const int w4 = warp - 4, row = 32 * w4 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(32 * w4) << 16);
-    uint32_t tcount = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+    uint32_t pp = 0;                                               // chunk-pair counter over the CTA's whole work list
+    const int npairs = (a.kchunks + 1) / 2;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int mt = (int)(tile / a.ntiles_n), nt = (int)(tile - (long long)mt * a.ntiles_n);
       const int b = mt / a.mtiles_per_b, l = a.l0 + (mt - b * a.mtiles_per_b) * 128 + row;
       const bool pv = l < a.l0 + a.ln;
-      const int dbuf = tcount & 1;
-      tc::mbar_wait_u(D_FULL(dbuf), (tcount >> 1) & 1);
-      tc::fence_after_sync();
-#pragma unroll 1
-      for (int c0 = 0; c0 < NT; c0 += 32) {
-        uint32_t r[32];
-        tc::tmem_ld32_nowait(lane_addr + dbuf * C::D_COLS + c0, r);
-        tc::tmem_wait_ld();
-        const int n0 = nt * NT + c0;
-        if (n0 >= a.N) break;
-        if constexpr (OUT == OUT_CH) {
-          float* dst = a.out + ((size_t)b * a.N + n0) * a.L + l;
+      float acc[NT];
+      for (int pr = 0; pr < npairs; ++pr, ++pp) {
+        const int dbuf = pp & 1;
+        timed_wait(D_FULL(dbuf), (pp >> 1) & 1, 1);
+        tc::fence_after_sync();
+        const long long tD0 = dbg_on ? clock64() : 0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (pv && n0 + j < a.N) {
-              float v = __uint_as_float(r[j]);
-              if (a.bias) v += __ldg(a.bias + n0 + j);
+        for (int c0 = 0; c0 < NT; c0 += 32) {
+          uint32_t r[32];
+          tc::tmem_ld32_nowait(lane_addr + dbuf * C::D_COLS + c0, r);
+          tc::tmem_wait_ld();
+          if (pr == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[c0 + j] = __uint_as_float(r[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+          }
+        }
+        tc::fence_before_sync();
+        tc::mbar_arrive(D_EMPTY(dbuf));
+        if (dbg_on) dbg_t[2] += clock64() - tD0;
+      }
+      const long long tS0 = dbg_on ? clock64() : 0;
+      const int nbase = nt * NT;
+      if constexpr (OUT == OUT_CH) {
+        float* dst = a.out + ((size_t)b * a.N + nbase) * a.L + l;
+        if (nbase + NT <= a.N && a.bias == nullptr) {               // full tile: plain strided stores (warp = 128 bytes each)
+          if (pv) {
+#pragma unroll
+            for (int j = 0; j < NT; ++j) { *dst = acc[j]; dst += a.L; }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < NT; ++j) {
+            if (pv && nbase + j < a.N) {
+              float v = acc[j];
+              if (a.bias) v += __ldg(a.bias + nbase + j);
               dst[(size_t)j * a.L] = v;
             }
           }
-        } else {
-          float* dst = a.out + ((size_t)b * a.L + l) * a.N + n0;
-          if (pv) {
-            if (n0 + 32 <= a.N && (a.N & 3) == 0) {
+        }
+      } else {
+        float* dst = a.out + ((size_t)b * a.L + l) * a.N + nbase;
+        if (pv) {
+          if (nbase + NT <= a.N && (a.N & 3) == 0) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                                       __uint_as_float(r[4 * j + 3]));
-                if (a.bias) {
-                  const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + n0) + j);
-                  v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
-                }
-                reinterpret_cast<float4*>(dst)[j] = v;
+            for (int j = 0; j < NT / 4; ++j) {
+              float4 v = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+              if (a.bias) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + nbase) + j);
+                v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
               }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (n0 + j < a.N) dst[j] = __uint_as_float(r[j]) + (a.bias ? __ldg(a.bias + n0 + j) : 0.f);
+              reinterpret_cast<float4*>(dst)[j] = v;
             }
+          } else {
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+              if (nbase + j < a.N) dst[j] = acc[j] + (a.bias ? __ldg(a.bias + nbase + j) : 0.f);
           }
         }
       }
-      tc::fence_before_sync();
-      tc::mbar_arrive(D_EMPTY(dbuf));
+      if (dbg_on) dbg_t[3] += clock64() - tS0;
     }
+    if (dbg_on && tid == 128) { a.dbg[2] = dbg_t[1]; a.dbg[3] = dbg_t[2]; a.dbg[15] = dbg_t[3]; }
   } else if (warp == 8) {
     // ================================================================== bulk-copy producer (one thread)
     if (lane == 0) {
@@ -328,44 +412,51 @@ __global__ void __launch_bounds__(kThreads, 1) proj_gemm_kernel(const Args a) {
         const int mt = (int)(tile / a.ntiles_n), nt = (int)(tile - (long long)mt * a.ntiles_n);
         for (int kc = 0; kc < a.kchunks; ++kc, ++it) {
           const int s = it % C::STAGES;
-          tc::mbar_wait_u(B_EMPTY(s), ((it / C::STAGES) & 1) ^ 1);
+          timed_wait(B_EMPTY(s), ((it / C::STAGES) & 1) ^ 1, 2);
           tc::mbar_arrive_expect_tx(B_FULL(s), C::STAGE_BYTES);
           const float* src = a.wimg + ((size_t)nt * a.kchunks + kc) * (C::STAGE_BYTES / 4);
           tc::bulk_g2s(sbase + s * C::STAGE_BYTES, src, C::STAGE_BYTES, B_FULL(s));
         }
       }
+      if (dbg_on) { a.dbg[4] = dbg_t[2]; a.dbg[5] = clock64() - dbg_start; }
     }
   } else {
     // ================================================================== MMA issuer (one thread)
     if (lane == 0) {
       constexpr uint32_t idesc = tc::make_idesc(NT);
-      uint32_t it = 0, tcount = 0;
-      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
-        const int dbuf = tcount & 1;
-        tc::mbar_wait_u(D_EMPTY(dbuf), ((tcount >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
-        tc::fence_after_sync();
-        const uint32_t dcol = tmem + dbuf * C::D_COLS;
-        for (int kc = 0; kc < a.kchunks; ++kc, ++it) {
-          const int s = it % C::STAGES, abuf = it & 1;
-          tc::mbar_wait_u(B_FULL(s), (it / C::STAGES) & 1);
-          tc::mbar_wait_u(A_FULL(abuf), (it >> 1) & 1);
+      uint32_t it = 0, pp = 0;
+      const int npairs = (a.kchunks + 1) / 2;
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int pr = 0; pr < npairs; ++pr, ++pp) {
+          const int dbuf = pp & 1;
+          timed_wait(D_EMPTY(dbuf), ((pp >> 1) & 1) ^ 1, 3);       // the epilogue has drained this accumulator
           tc::fence_after_sync();
-          const uint32_t bhi = sbase + s * C::STAGE_BYTES, blo = bhi + C::STAGE_BYTES / 2;
-          const uint32_t ahi = tmem + C::A_COL0 + abuf * 64, alo = ahi + 32;
+          const uint32_t dcol = tmem + dbuf * C::D_COLS;
+          const int kc_end = min(a.kchunks, 2 * pr + 2);
+          for (int kc = 2 * pr; kc < kc_end; ++kc, ++it) {
+            const int s = it % C::STAGES, abuf = it & 1;
+            timed_wait(B_FULL(s), (it / C::STAGES) & 1, 4);
+            timed_wait(A_FULL(abuf), (it >> 1) & 1, 5);
+            tc::fence_after_sync();
+            const uint32_t bhi = sbase + s * C::STAGE_BYTES, blo = bhi + C::STAGE_BYTES / 2;
+            const uint32_t ahi = tmem + C::A_COL0 + abuf * 64, alo = ahi + 32;
 #pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t aa = (pass == 1) ? alo : ahi;
-            const uint32_t bb = (pass == 2) ? blo : bhi;
+            for (int pass = 0; pass < 3; ++pass) {
+              const uint32_t aa = (pass == 1) ? alo : ahi;
+              const uint32_t bb = (pass == 2) ? blo : bhi;
 #pragma unroll
-            for (int ks = 0; ks < kKC / 8; ++ks)
-              tc::mma_tf32_ts(dcol, aa + 8 * ks, tc::make_desc_ls(bb + ks * 2 * kLBO, kLBO, kSBO), idesc,
-                              (kc | pass | ks) ? 1u : 0u);
+              for (int ks = 0; ks < kKC / 8; ++ks)
+                tc::mma_tf32_ts(dcol, aa + 8 * ks, tc::make_desc_ls(bb + ks * 2 * kLBO, kLBO, kSBO), idesc,
+                                ((kc - 2 * pr) | pass | ks) ? 1u : 0u);
+            }
+            tc::mma_commit(A_EMPTY(abuf));                         // A chunk buffer free once these MMAs complete
+            tc::mma_commit(B_EMPTY(s));                            // and so is the weight stage
           }
-          tc::mma_commit(A_EMPTY(abuf));                           // A chunk buffer free once these MMAs complete
-          tc::mma_commit(B_EMPTY(s));                              // and so is the weight stage
+          tc::mma_commit(D_FULL(dbuf));
         }
-        tc::mma_commit(D_FULL(dbuf));
       }
+      if (dbg_on) { a.dbg[6] = dbg_t[3]; a.dbg[7] = dbg_t[4]; a.dbg[8] = dbg_t[5]; a.dbg[9] = clock64() - dbg_start;
+                    a.dbg[10] = nchunks; }
     }
   }
 
@@ -389,11 +480,17 @@ __global__ void __launch_bounds__(kThreads, 1) proj_gemm_kernel(const Args a) {
 //               staged rows into hi / lo K-major core-matrix images (one 16-byte piece = four consecutive positions of
 //               one row; optional transposed short filter on the fly from six staged samples)
 //   staging   both chunks arrive by cp.async into shared-memory rings, three chunks in flight
-//   split-K   CTA = (n tile, m tile, slice of the position chunks); accumulator (128 x 128) in TMEM for the whole
-//             slice, one partial per CTA, summed in fixed order by wgrad_reduce_kernel (deterministic, no atomics).
+//   split-K   CTA = (n tile, m tile, slice of the position chunks), one partial per CTA, summed in fixed order by
+//             wgrad_reduce_kernel (deterministic, no atomics).
+//   accuracy  the tensor core adds into its accumulator with truncation: a chain of n MMAs biases the sum by ~n 2^-24
+//             towards zero, and a slice here is ~8000 MMAs long (measured: four digits lost).  So (i) the hi*hi products
+//             go to a MAIN accumulator that is restarted every kSeg chunks (two TMEM buffers in turn) and drained by four
+//             extra warps into the CTA's partial in L2 with round-to-nearest adds, (ii) the lo*hi + hi*lo products go to a
+//             separate CORRECTION accumulator, 2^-11 times smaller, whose own bias is negligible over the whole slice.
 namespace wg {
 
-constexpr int kThreads = 288;             // warps 0-3 Y staging + A conversion + epilogue, 4-7 X staging + B images, 8 MMA
+constexpr int kThreads = 416;             // warps 0-3 Y staging + A conversion, 4-7 X staging + B images, 8 MMA, 9-12 drain
+constexpr int kSeg = 8;                   // chunks per accumulation segment (32 chained main MMAs)
 constexpr int kStg = 3;                   // staged chunks in flight
 constexpr uint32_t kYPitch = 132 * 4;     // staged Y row: 128 columns (+pad)
 constexpr uint32_t kYStage = 32 * kYPitch;            // 32 positions
@@ -420,18 +517,22 @@ struct Args {
 __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
-  // barriers: b_full[2] b_empty[2] a_full[2] a_empty[2] d_full
-  uint32_t* tmem_p = reinterpret_cast<uint32_t*>(bars + 9);
+  // barriers: b_full[2] b_empty[2] a_full[2] a_empty[2] dm_full[2] dm_empty[2] dc_full
+  uint32_t* tmem_p = reinterpret_cast<uint32_t*>(bars + 13);
   const uint32_t sbase = tc::smem_u32(smem), bar0 = tc::smem_u32(bars);
   auto B_FULL = [&](int s) { return bar0 + 8u * s; };
   auto B_EMPTY = [&](int s) { return bar0 + 8u * (2 + s); };
   auto A_FULL = [&](int j) { return bar0 + 8u * (4 + j); };
   auto A_EMPTY = [&](int j) { return bar0 + 8u * (6 + j); };
-  const uint32_t D_FULL = bar0 + 8u * 8;
+  auto DM_FULL = [&](int j) { return bar0 + 8u * (8 + j); };
+  auto DM_EMPTY = [&](int j) { return bar0 + 8u * (10 + j); };
+  const uint32_t DC_FULL = bar0 + 8u * 12;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // tensor memory map (columns): main accumulators [0,128) [128,256), correction accumulator [256,384), A chunks [384,512)
+  constexpr uint32_t kColDC = 256, kColA = 384;
 
   if (warp == 8) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_p)), "r"(256)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_p)), "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -439,8 +540,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a) {
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(B_FULL(s), 128); tc::mbar_init(B_EMPTY(s), 1);
       tc::mbar_init(A_FULL(s), 128); tc::mbar_init(A_EMPTY(s), 1);
+      tc::mbar_init(DM_FULL(s), 1); tc::mbar_init(DM_EMPTY(s), 128);
     }
-    tc::mbar_init(D_FULL, 1);
+    tc::mbar_init(DC_FULL, 1);
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -461,25 +563,37 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a) {
   if (warp < 4) {
     // ---------------------------------------------------------------- A side: thread = column n of Y = TMEM lane
     const uint32_t lane_addr = tmem + ((uint32_t)(32 * warp) << 16);
+    // chunk cursor (batch, first position), advanced incrementally: no 64-bit divisions in the loop
+    int sb_ = (int)(c_begin / a.chunks_per_b), sl_ = (int)(c_begin - (long long)sb_ * a.chunks_per_b) * 32;
     auto stage = [&](long long q) {                                     // Y[l0 .. l0+32)[n0 .. n0+128) -> slot q % kStg
-      const long long c = c_begin + q;
-      const int b = (int)(c / a.chunks_per_b), l0 = (int)(c - (long long)b * a.chunks_per_b) * 32;
+      const int b = sb_, l0 = sl_;
+      sl_ += 32;
+      if (sl_ >= a.chunks_per_b * 32) { sl_ = 0; ++sb_; }
       unsigned char* st = smem + kOffY + (size_t)(q % kStg) * kYStage;
-      for (int p = tid; p < 32 * 32; p += 128) {
-        const int k = p >> 5, qd = p & 31;
-        const int l = l0 + k, n = n0 + 4 * qd;
-        const float* src = a.Y + ((size_t)b * a.L + (l < a.L ? l : 0)) * a.N;
-        unsigned char* dst = st + k * kYPitch + qd * 16;
-        if (a.vec) {
-          const bool ok = (l < a.L) && (n + 4 <= a.N);
-          cp_async16(dst, src + (ok ? n : 0), ok);
-        } else {
-          float4 v;
-          v.x = (l < a.L && n + 0 < a.N) ? __ldg(src + n + 0) : 0.f;
-          v.y = (l < a.L && n + 1 < a.N) ? __ldg(src + n + 1) : 0.f;
-          v.z = (l < a.L && n + 2 < a.N) ? __ldg(src + n + 2) : 0.f;
-          v.w = (l < a.L && n + 3 < a.N) ? __ldg(src + n + 3) : 0.f;
-          *reinterpret_cast<float4*>(dst) = v;
+      const int k0_ = tid >> 5, q32 = tid & 31;                          // pieces (position k0_ + 4 i, quad q32), i < 8
+      if (a.vec && l0 + 32 <= a.L && n0 + 128 <= a.N) {                  // interior chunk: no predicates
+        const float* src = a.Y + ((size_t)b * a.L + l0 + k0_) * a.N + n0 + 4 * q32;
+        unsigned char* dst = st + k0_ * kYPitch + q32 * 16;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cp_async16(dst + i * 4 * kYPitch, src + (size_t)i * 4 * a.N, true);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int k = k0_ + 4 * i, qd = q32;
+          const int l = l0 + k, n = n0 + 4 * qd;
+          const float* src = a.Y + ((size_t)b * a.L + (l < a.L ? l : 0)) * a.N;
+          unsigned char* dst = st + k * kYPitch + qd * 16;
+          if (a.vec) {
+            const bool ok = (l < a.L) && (n + 4 <= a.N);
+            cp_async16(dst, src + (ok ? n : 0), ok);
+          } else {
+            float4 v;
+            v.x = (l < a.L && n + 0 < a.N) ? __ldg(src + n + 0) : 0.f;
+            v.y = (l < a.L && n + 1 < a.N) ? __ldg(src + n + 1) : 0.f;
+            v.z = (l < a.L && n + 2 < a.N) ? __ldg(src + n + 2) : 0.f;
+            v.w = (l < a.L && n + 3 < a.N) ? __ldg(src + n + 3) : 0.f;
+            *reinterpret_cast<float4*>(dst) = v;
+          }
         }
       }
       cp_async_commit();
@@ -504,7 +618,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a) {
       const int buf = it & 1;
       tc::mbar_wait_u(A_EMPTY(buf), ((it >> 1) & 1) ^ 1);
       tc::fence_after_sync();
-      const uint32_t acol = 128 + buf * 64;
+      const uint32_t acol = kColA + buf * 64;
       tc::tmem_st32(lane_addr + acol, hi);
       tc::tmem_st32(lane_addr + acol + 32, lo);
       tc::tmem_wait_st();
@@ -512,39 +626,17 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a) {
       tc::mbar_arrive(A_FULL(buf));
     }
     cp_async_wait_all();
-    // ---------------------------------------------------------------- epilogue: partial sums of this slice
-    if (nchunks > 0) {
-      tc::mbar_wait_u(D_FULL, 0);
-      tc::fence_after_sync();
-    }
-    const bool nv = tid < nrows;
-    float* dst = a.part + ((size_t)split * a.N + (nv ? n0 + tid : 0)) * a.M + m0;
-#pragma unroll 1
-    for (int c0 = 0; c0 < 128; c0 += 32) {
-      uint32_t r[32];
-      if (nchunks > 0) { tc::tmem_ld32_nowait(lane_addr + c0, r); tc::tmem_wait_ld(); }
-      else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = 0u;
-      }
-      if (nv) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c0 + j < mcols) dst[c0 + j] = __uint_as_float(r[j]);
-      }
-    }
-    tc::fence_before_sync();
   } else if (warp < 8) {
     // ---------------------------------------------------------------- B side: X rows -> K-major hi / lo images
     const int t = tid - 128;
     const bool use_fir = a.fir != nullptr;
+    int sb_ = (int)(c_begin / a.chunks_per_b), sl_ = (int)(c_begin - (long long)sb_ * a.chunks_per_b) * 32;
     auto stage = [&](long long q) {                                     // X[m0 .. m0+128)[l0 .. l0+32(+4)) -> slot q % kStg
-      const long long c = c_begin + q;
-      const int b = (int)(c / a.chunks_per_b), l0 = (int)(c - (long long)b * a.chunks_per_b) * 32;
+      const int b = sb_, l0 = sl_;
+      sl_ += 32;
+      if (sl_ >= a.chunks_per_b * 32) { sl_ = 0; ++sb_; }
       unsigned char* st = smem + kOffX + (size_t)(q % kStg) * kXStage;
-      for (int p = t; p < 128 * 9; p += 128) {
-        const int r = p / 9, qd = p - r * 9;
-        if (qd == 8 && !use_fir) continue;
+      auto piece = [&](int r, int qd) {
         const int m = m0 + r, l = l0 + 4 * qd;
         const float* src = a.X + ((size_t)b * a.M + (m < a.M ? m : 0)) * a.L;
         unsigned char* dst = st + r * kXPitch + qd * 16;
@@ -559,6 +651,20 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a) {
           v.w = (m < a.M && l + 3 < a.L) ? __ldg(src + l + 3) : 0.f;
           *reinterpret_cast<float4*>(dst) = v;
         }
+      };
+      // 128 rows x 8 quads (row (t >> 3) + 16 i, quad t & 7), eight pieces per thread, plus the look-ahead quad of row t
+      // (fused FIR)
+      if (a.vec && m0 + 128 <= a.M && l0 + 32 + (use_fir ? 4 : 0) <= a.L) {   // interior chunk: no predicates
+        const float* base = a.X + ((size_t)b * a.M + m0) * a.L + l0;
+        const float* src = base + (size_t)(t >> 3) * a.L + 4 * (t & 7);
+        unsigned char* dst = st + (t >> 3) * kXPitch + (t & 7) * 16;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cp_async16(dst + i * 16 * kXPitch, src + (size_t)i * 16 * a.L, true);
+        if (use_fir) cp_async16(st + t * kXPitch + 128, base + (size_t)t * a.L + 32, true);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) piece((t >> 3) + 16 * i, t & 7);
+        if (use_fir) piece(t, 8);
       }
       cp_async_commit();
     };
@@ -615,35 +721,95 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a) {
     cp_async_wait_all();
   } else {
     // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    if (warp == 8 && lane == 0) {
       constexpr uint32_t idesc = tc::make_idesc(128);
       for (long long q = 0; q < nchunks; ++q) {
         const uint32_t it = (uint32_t)q;
         const int s = it & 1;
+        const uint32_t seg = it / kSeg, sb = seg & 1;
+        if (it % kSeg == 0) {                                           // new segment: its main accumulator must be drained
+          tc::mbar_wait_u(DM_EMPTY(sb), ((seg >> 1) & 1) ^ 1);
+          tc::fence_after_sync();
+        }
         tc::mbar_wait_u(B_FULL(s), (it >> 1) & 1);
         tc::mbar_wait_u(A_FULL(s), (it >> 1) & 1);
         tc::fence_after_sync();
         const uint32_t bhi = sbase + kOffImg + s * 2 * kImg, blo = bhi + kImg;
-        const uint32_t ahi = tmem + 128 + s * 64, alo = ahi + 32;
+        const uint32_t ahi = tmem + kColA + s * 64, alo = ahi + 32;
 #pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t aa = (pass == 1) ? alo : ahi;
-          const uint32_t bb = (pass == 2) ? blo : bhi;
+        for (int ks = 0; ks < 4; ++ks)                                  // main: hi * hi
+          tc::mma_tf32_ts(tmem + sb * 128, ahi + 8 * ks, tc::make_desc_ls(bhi + ks * 2 * pg::kLBO, pg::kLBO, pg::kSBO), idesc,
+                          ((it % kSeg) | ks) ? 1u : 0u);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            tc::mma_tf32_ts(tmem, aa + 8 * ks, tc::make_desc_ls(bb + ks * 2 * pg::kLBO, pg::kLBO, pg::kSBO), idesc,
-                            (it | pass | ks) ? 1u : 0u);
-        }
+        for (int ks = 0; ks < 4; ++ks)                                  // correction: lo * hi
+          tc::mma_tf32_ts(tmem + kColDC, alo + 8 * ks, tc::make_desc_ls(bhi + ks * 2 * pg::kLBO, pg::kLBO, pg::kSBO), idesc,
+                          (it | ks) ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)                                  //             hi * lo
+          tc::mma_tf32_ts(tmem + kColDC, ahi + 8 * ks, tc::make_desc_ls(blo + ks * 2 * pg::kLBO, pg::kLBO, pg::kSBO), idesc, 1u);
         tc::mma_commit(A_EMPTY(s));
         tc::mma_commit(B_EMPTY(s));
+        if (it % kSeg == kSeg - 1 || q + 1 == nchunks) tc::mma_commit(DM_FULL(sb));
       }
-      if (nchunks > 0) tc::mma_commit(D_FULL);
+      if (nchunks > 0) tc::mma_commit(DC_FULL);
+    }
+  }
+  if (warp >= 9) {
+    // ---------------------------------------------------------------- drain warps: thread = accumulator row (TMEM lane)
+    const int w4 = warp - 9, row = 32 * w4 + lane;                      // warps 9..12 -> lane quadrants 1,2,3,0
+    const int lq = warp & 3;
+    const int n = 32 * lq + lane;                                       // accumulator row of this thread
+    (void)w4; (void)row;
+    const uint32_t lane_addr = tmem + ((uint32_t)(32 * lq) << 16);
+    const bool nv = n < nrows;
+    float* dst = a.part + ((size_t)split * a.N + (nv ? n0 + n : 0)) * a.M + m0;
+    const bool v4 = ((a.M & 3) == 0) && (mcols == 128);
+    const uint32_t nseg = (uint32_t)((nchunks + kSeg - 1) / kSeg);
+    auto add_cols = [&](uint32_t col0, bool first) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t r[32];
+        tc::tmem_ld32_nowait(lane_addr + col0 + c0, r);
+        tc::tmem_wait_ld();
+        if (!nv) continue;
+        if (v4) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                   __uint_as_float(r[4 * j + 3]));
+            float4* pd = reinterpret_cast<float4*>(dst + c0) + j;
+            if (!first) { const float4 o = *pd; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+            *pd = v;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < mcols) dst[c0 + j] = __uint_as_float(r[j]) + (first ? 0.f : dst[c0 + j]);
+        }
+      }
+    };
+    if (nchunks == 0) {
+      if (nv)
+        for (int c = 0; c < mcols; ++c) dst[c] = 0.f;
+    } else {
+      for (uint32_t seg = 0; seg < nseg; ++seg) {
+        const int sb = seg & 1;
+        tc::mbar_wait_u(DM_FULL(sb), (seg >> 1) & 1);
+        tc::fence_after_sync();
+        add_cols(sb * 128, seg == 0);
+        tc::fence_before_sync();
+        tc::mbar_arrive(DM_EMPTY(sb));
+      }
+      tc::mbar_wait_u(DC_FULL, 0);
+      tc::fence_after_sync();
+      add_cols(kColDC, false);
+      tc::fence_before_sync();
     }
   }
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 8) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
   }
 }
 

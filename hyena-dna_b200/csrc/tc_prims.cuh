@@ -6,10 +6,11 @@
 namespace hy {
 namespace tc {
 
+// Round-to-nearest (ties away) to tf32 by integer arithmetic: add half an ulp of the 10-bit mantissa, clear the 13 low
+// bits.  Same result as cvt.rna.tf32.f32 for finite inputs (Inf stays Inf, NaN stays NaN); ptxas expands that PTX
+// instruction into five SASS instructions (add, |x| < Inf test, select, mask), this is two.
 __device__ __forceinline__ float to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = to_tf32(x);
@@ -55,7 +56,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred P1;\n\t"
       "LAB_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
       "@P1 bra DONE;\n\t"
       "bra LAB_WAIT;\n\t"
       "DONE:\n\t}\n"
@@ -148,14 +149,16 @@ __device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, ui
                : "memory");
 }
 // wait (no PTX labels: may be inlined any number of times); traps after ~2 s of waiting instead of hanging the GPU --
-// a protocol bug then surfaces as a launch failure
+// a protocol bug then surfaces as a launch failure.  No suspend-time hint: with the 10 ms hint round 1 used, ptxas emits
+// SYNCS.PHASECHK + NANOSLEEP 0x989680 and the sleeping warp wakes late -- ncu put 16-32 % of all stall samples of the
+// projection kernels on that NANOSLEEP (profiles/r2_ncu_proj_staged_stalls.txt)
 __device__ __forceinline__ void mbar_wait_u(uint32_t mbar, uint32_t parity) {
   uint32_t done = 0;
   const long long t0 = clock64();
   while (!done) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(done)
         : "r"(mbar), "r"(parity)

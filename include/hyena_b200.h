@@ -186,6 +186,8 @@ HY_API size_t hyena_b200_proj_wgrad_scratch_bytes(int M, int N);
 HY_API int hyena_b200_proj_wgrad(const float* X, const float* Y, const float* fir, float* dW, int transposed_out, float beta,
                           int B, int L, int M, int N, void* scratch, size_t scratch_bytes, void* stream);
 HY_API size_t hyena_b200_proj_wimg_bytes(int N, int K);
+/* debug aid (tools/dbg_proj_timing.py): device buffer of >= 16 int64 receiving per-role barrier-wait cycle counters */
+HY_API int hyena_b200_proj_debug_buffer(void* buf);
 HY_API int hyena_b200_proj_gemm(const float* act, int act_layout, const float* W, int ldw, int w_transposed,
                          const float* bias, const float* fir, float* out, int out_layout, int B, int L, int K, int N,
                          int l_begin, int l_len, void* wimg, size_t wimg_bytes, void* stream);
