@@ -28,7 +28,8 @@ constexpr int kTileM = 128;
 constexpr uint32_t kSBO = 2048, kLBO = 128;
 constexpr int kImgW64 = 64 * 64;            // floats of a 64-row operand image
 constexpr int kImgW128 = 128 * 64;          // floats of a 128-row operand image
-constexpr int kTmemCols = 256;              // [0,64) hidden-layer accumulator, [64,192) output half accumulator
+constexpr int kTmemCols = 512;              // main accumulators: [0,64) hidden layer, [64,192) output half; correction ones at +256
+constexpr uint32_t kCorr = 256;             // column offset of the correction accumulator of each main accumulator
 
 __host__ __device__ constexpr uint32_t op_off(int r, int k) {   // byte offset inside an operand image
   return (uint32_t)((r >> 3) * 2048 + (k >> 2) * 128 + (r & 7) * 16 + (k & 3) * 4);
@@ -48,22 +49,40 @@ __host__ __device__ constexpr size_t wimg_floats(int D) { return 4 * (size_t)kIm
 __device__ __noinline__ float sin_ni(float x) { return sinf(x); }
 __device__ __noinline__ float cos_ni(float x) { return cosf(x); }
 
-// D[128 x N] (+)= A * B^T as 3xTF32: 24 MMAs of K = 8, issued by the calling (single) thread
+// D[128 x N] = A * B^T as 3xTF32: 24 MMAs of K = 8, issued by the calling (single) thread.  The tensor core adds into
+// its accumulator with truncation, so a chain of n MMAs biases the sum by ~n 2^-24 towards zero (measured: the filter came
+// out 6x less accurate than the reference's fp32 path with all 24 products chained into one accumulator).  Hence two
+// accumulators: the eight hi*hi products go to tmem_d, the sixteen lo*hi / hi*lo products (2^-11 times smaller, their
+// bias is negligible) to tmem_d + kCorr; the epilogues add the two (ld_acc16 / ld_acc32).
 __device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
                                             int N, uint32_t mbar) {
   const uint32_t idesc = make_idesc(N);
-  uint32_t acc = 0;
 #pragma unroll
   for (int pass = 0; pass < 3; ++pass) {
     const uint32_t a = (pass == 1) ? a_lo : a_hi;
     const uint32_t b = (pass == 2) ? b_lo : b_hi;
+    const uint32_t d = (pass == 0) ? tmem_d : tmem_d + kCorr;
 #pragma unroll
-    for (int ks = 0; ks < 8; ++ks) {
-      mma_tf32(tmem_d, make_desc(a + ks * 2 * kLBO), make_desc(b + ks * 2 * kLBO), idesc, acc);
-      acc = 1;
-    }
+    for (int ks = 0; ks < 8; ++ks)
+      mma_tf32(d, make_desc(a + ks * 2 * kLBO), make_desc(b + ks * 2 * kLBO), idesc, (ks > 0 || pass == 2) ? 1u : 0u);
   }
   mma_commit(mbar);
+}
+
+// main + correction accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void ld_acc16(uint32_t taddr, float (&v)[16]) {
+  float c[16];
+  tmem_ld16(taddr, v);
+  tmem_ld16(taddr + kCorr, c);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] += c[i];
+}
+__device__ __forceinline__ void ld_acc32(uint32_t taddr, float (&v)[32]) {
+  float c[32];
+  tmem_ld32(taddr, v);
+  tmem_ld32(taddr + kCorr, c);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] += c[i];
 }
 
 // write NV activations (features k0 .. k0+NV) of row `row` as hi/lo operand images
@@ -203,7 +222,7 @@ filter_tc_fwd_kernel(const FilterParams P, const float* __restrict__ wimg, float
       fence_after_sync();
       const float* bs = layer ? b2s : b1s;
       float a[16];
-      tmem_ld16(lane_addr + part * 16, a);
+      ld_acc16(lane_addr + part * 16, a);
 #pragma unroll
       for (int j = 0; j < 16; ++j) a[j] = sin_ni(frs[part * 16 + j] * (a[j] + bs[part * 16 + j]));
       store_row_split<16>(smem, row, part * 16, a);        // the MMAs that read the A images have completed
@@ -229,7 +248,7 @@ filter_tc_fwd_kernel(const FilterParams P, const float* __restrict__ wimg, float
         for (int i = tid; i < 2 * kImgW128 / 4; i += kThreads) cp_async16(smem + kOffW3hi + 16 * i, src + 4 * i, true);
       }
       float v[32];
-      tmem_ld32(lane_addr + 64 + part * 32, v);
+      ld_acc32(lane_addr + 64 + part * 32, v);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int c = h * 128 + part * 32 + j;
@@ -381,7 +400,7 @@ filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const
     }
     mbar_wait(mbar, phase); phase ^= 1;
     fence_after_sync();
-    tmem_ld16(lane_addr + part * 16, pre2);
+    ld_acc16(lane_addr + part * 16, pre2);
 #pragma unroll
     for (int j = 0; j < 16; ++j) { pre2[j] += b1s[part * 16 + j]; a[j] = sin_ni(fr[j] * pre2[j]); }
     store_row_split<16>(smem, row, part * 16, a);
@@ -395,7 +414,7 @@ filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const
     }
     mbar_wait(mbar, phase); phase ^= 1;
     fence_after_sync();
-    tmem_ld16(lane_addr + part * 16, pre3);
+    ld_acc16(lane_addr + part * 16, pre3);
 #pragma unroll
     for (int j = 0; j < 16; ++j) { pre3[j] += b2s[part * 16 + j]; a[j] = sin_ni(fr[j] * pre3[j]); }
     if (tv) store16(out + 2 * arr, P.L, a);
@@ -428,16 +447,15 @@ filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const
         fence_after_sync();
         const uint32_t sb = sbase + kOffW3hi + (q & 1) * 32768;
         const uint32_t idesc = make_idesc(64);
-        uint32_t acc = q > 0 ? 1u : 0u;
 #pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
           const uint32_t aa = sbase + ((pass == 1) ? kOffAlo : kOffAhi);
           const uint32_t bb = sb + ((pass == 2) ? 16384u : 0u);
+          const uint32_t dd = (pass == 0) ? tmem : tmem + kCorr;      // main / correction accumulator (see issue_layer)
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            mma_tf32(tmem, make_desc(aa + ks * 2 * kLBO), make_desc(bb + ks * 2 * kLBO), idesc, acc);
-            acc = 1;
-          }
+          for (int ks = 0; ks < 8; ++ks)
+            mma_tf32(dd, make_desc(aa + ks * 2 * kLBO), make_desc(bb + ks * 2 * kLBO), idesc,
+                     (q > 0 || ks > 0 || pass == 2) ? 1u : 0u);
         }
         mma_commit(mbar);
       }
@@ -455,7 +473,7 @@ filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const
 
     // ---- layer 3 -> 2 -> 1 backward through the sine activations
     float X[16], da[16];
-    tmem_ld16(lane_addr + part * 16, da);
+    ld_acc16(lane_addr + part * 16, da);
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const float cs = cos_ni(fr[j] * pre3[j]);
@@ -476,7 +494,7 @@ filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const
     }
     mbar_wait(mbar, phase); phase ^= 1;
     fence_after_sync();
-    tmem_ld16(lane_addr + part * 16, da);
+    ld_acc16(lane_addr + part * 16, da);
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const float cs = cos_ni(fr[j] * pre2[j]);
@@ -496,7 +514,7 @@ filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const
     }
     mbar_wait(mbar, phase); phase ^= 1;
     fence_after_sync();
-    tmem_ld16(lane_addr + part * 16, da);
+    ld_acc16(lane_addr + part * 16, da);
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const float cs = cos_ni(fr[j] * pre1[j]);

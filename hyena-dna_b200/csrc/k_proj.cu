@@ -85,7 +85,7 @@ cudaError_t launch_proj_wgrad(const float* X, const float* Y, const float* fir, 
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   wg::Args a;
-  a.X = X; a.Y = Y; a.fir = fir; a.part = part; a.B = B; a.L = L; a.M = M; a.N = N;
+  a.X = X; a.Y = Y; a.fir = fir; a.part = part; a.dbg = g_proj_dbg; a.B = B; a.L = L; a.M = M; a.N = N;
   a.chunks_per_b = (L + 31) / 32;
   proj_wgrad_plan(M, N, sms, &a.mtiles, &a.ntiles, &a.splits);
   const long long total_chunks = (long long)B * a.chunks_per_b;

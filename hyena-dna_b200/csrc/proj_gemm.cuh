@@ -21,8 +21,8 @@
 //             error of cuBLASLt's BF16x9 on y at L = 2^20, the 2^20-position weight gradients lost four digits.
 //   3xTF32    x = hi + lo, hi = rna_tf32(x), lo = rna_tf32(x - hi);  D += Ahi Bhi + Alo Bhi + Ahi Blo   (lo*lo < 2^-22)
 //
-// Warp roles (320 threads): warps 0-3 stage + convert (thread = position), warps 4-7 epilogue (thread = position),
-// warp 8 lane 0 bulk-copy producer, warp 9 lane 0 MMA issuer.
+// Warp roles (352 threads): warps 0-3 stage + convert (thread = position), warps 4-7 epilogue (thread = position),
+// warp 8 lane 0 bulk-copy producer, warps 9 and 10 lane 0 MMA issuers (alternate chunk pairs).
 //
 // Optional fused prologue (FIR): the activation is ds (B, C, L) and the GEMM consumes dp = transposed 3-tap depthwise
 // filter of ds (dp[t] = w2 ds[t] + w1 ds[t+1] + w0 ds[t+2], hyena.py:363-369 backward), so dp never exists in HBM.
@@ -36,7 +36,7 @@ namespace hy {
 namespace pg {
 
 constexpr int kKC = 32;                 // K chunk (one chunk = 4 MMAs of K = 8 per product)
-constexpr int kThreads = 320;
+constexpr int kThreads = 352;          // 11 warps: 4 convert, 4 epilogue, 1 bulk-copy producer, 2 MMA issuers
 constexpr int kAStages = 4;             // activation chunks in flight
 constexpr uint32_t kSBO = 1024, kLBO = 128;
 constexpr uint32_t kAPitchCh = 132 * 4; // ACT_CH staging row: 128 positions + one look-ahead quad (fused FIR)
@@ -102,8 +102,10 @@ template <int NT> struct Cfg {
   static constexpr size_t OFF_BAR = OFF_A + (size_t)kAStages * kAStageBytes;
   static constexpr size_t OFF_FIR = OFF_BAR + 256;
   static constexpr size_t SMEM = OFF_FIR;                              // + 12 K bytes of taps when the FIR is fused
-  static_assert(2 * NT + 128 <= 512, "two accumulators and two A (hi, lo) chunk buffers must fit tensor memory");
+  static_assert(2 * NT + 4 * 64 <= 512, "two accumulators and four A (hi, lo) chunk buffers must fit tensor memory");
   static_assert(NT == 128, "the epilogue keeps NT partial sums per thread in registers");
+  static_assert(STAGES == 4, "chunk c uses weight stage and A buffer c & 3: pair p (chunks 2p, 2p+1) then owns stages "
+                             "{0,1} or {2,3}, i.e. each of the two MMA issuers sees its barriers' phases in order");
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -115,17 +117,17 @@ __global__ void __launch_bounds__(kThreads, 1) proj_gemm_kernel(const Args a) {
   using C = Cfg<NT>;
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
-  // barrier map: b_full[S] b_empty[S] a_full[2] a_empty[2] d_full[2] d_empty[2]
-  uint32_t* tmem_p = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 8);
+  // barrier map: b_full[S] b_empty[S] a_full[4] a_empty[4] d_full[2] d_empty[2]
+  uint32_t* tmem_p = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 12);
   float* fir_s = reinterpret_cast<float*>(smem + C::OFF_FIR);     // (K, 3) taps, FIR only
   const uint32_t sbase = tc::smem_u32(smem);
   const uint32_t bar0 = tc::smem_u32(bars);
   auto B_FULL = [&](int s) { return bar0 + 8u * s; };
   auto B_EMPTY = [&](int s) { return bar0 + 8u * (C::STAGES + s); };
   auto A_FULL = [&](int j) { return bar0 + 8u * (2 * C::STAGES + j); };
-  auto A_EMPTY = [&](int j) { return bar0 + 8u * (2 * C::STAGES + 2 + j); };
-  auto D_FULL = [&](int j) { return bar0 + 8u * (2 * C::STAGES + 4 + j); };
-  auto D_EMPTY = [&](int j) { return bar0 + 8u * (2 * C::STAGES + 6 + j); };
+  auto A_EMPTY = [&](int j) { return bar0 + 8u * (2 * C::STAGES + 4 + j); };
+  auto D_FULL = [&](int j) { return bar0 + 8u * (2 * C::STAGES + 8 + j); };
+  auto D_EMPTY = [&](int j) { return bar0 + 8u * (2 * C::STAGES + 10 + j); };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool use_fir = (ACT == ACT_CH) && a.fir != nullptr;
@@ -138,10 +140,8 @@ __global__ void __launch_bounds__(kThreads, 1) proj_gemm_kernel(const Args a) {
     for (int i = tid; i < 3 * a.K; i += kThreads) fir_s[i] = __ldg(a.fir + i);
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) { tc::mbar_init(B_FULL(s), 1); tc::mbar_init(B_EMPTY(s), 1); }
-    for (int j = 0; j < 2; ++j) {
-      tc::mbar_init(A_FULL(j), 128); tc::mbar_init(A_EMPTY(j), 1);
-      tc::mbar_init(D_FULL(j), 1); tc::mbar_init(D_EMPTY(j), 128);
-    }
+    for (int j = 0; j < 4; ++j) { tc::mbar_init(A_FULL(j), 128); tc::mbar_init(A_EMPTY(j), 1); }
+    for (int j = 0; j < 2; ++j) { tc::mbar_init(D_FULL(j), 1); tc::mbar_init(D_EMPTY(j), 128); }
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -263,6 +263,8 @@ __global__ void __launch_bounds__(kThreads, 1) proj_gemm_kernel(const Args a) {
       cp_async_commit();
     };
 
+    const uint32_t spt = 2u * (uint32_t)((a.kchunks + 1) / 2);
+    uint32_t ccT = 0, ccT_next = 0, parAe = 0xFu;                   // tile ordinal of the conversion cursor; wait parities
     Cur cs, cc;                                                     // staging cursor, conversion cursor
     cur_set(cs, (int)blockIdx.x);
     cc = cs;
@@ -304,7 +306,8 @@ __global__ void __launch_bounds__(kThreads, 1) proj_gemm_kernel(const Args a) {
           }
         }
       }
-      cur_next(cc);
+      const int cc_kc = cc.kc;
+      { const int t0 = cc.tile; cur_next(cc); if (cc.tile != t0) ++ccT_next; }
       uint32_t hi[kKC], lo[kKC];
 #pragma unroll
       for (int j = 0; j < kKC; ++j) {
@@ -312,10 +315,13 @@ __global__ void __launch_bounds__(kThreads, 1) proj_gemm_kernel(const Args a) {
         tc::split_tf32(x[j], hh, lw);
         hi[j] = __float_as_uint(hh); lo[j] = __float_as_uint(lw);
       }
-      const uint32_t it = (uint32_t)q;
-      const int buf = it & 1;
+      // slot numbering shared by all roles: tile T of this CTA owns slots [T * spt, (T+1) * spt), spt = 2 * pairs per tile
+      // (even: with an odd number of chunks the last slot of a tile stays unused); slot -> A buffer / weight stage slot & 3
+      const uint32_t it = ccT * spt + (uint32_t)cc_kc;
+      const int buf = it & 3;
       long long tD = dbg_on ? clock64() : 0;
-      timed_wait(A_EMPTY(buf), ((it >> 1) & 1) ^ 1, 0);           // MMAs of the previous use of this buffer are done
+      timed_wait(A_EMPTY(buf), (parAe >> buf) & 1u, 0);           // MMAs of the previous use of this buffer are done
+      parAe ^= 1u << buf;
       tc::fence_after_sync();
       long long tE = dbg_on ? clock64() : 0;
       const uint32_t acol = C::A_COL0 + buf * 64;
@@ -325,6 +331,7 @@ __global__ void __launch_bounds__(kThreads, 1) proj_gemm_kernel(const Args a) {
       tc::fence_before_sync();
       tc::mbar_arrive(A_FULL(buf));
       if (dbg_on) { dbg_t[1] += tB - tA; dbg_t[2] += tC - tB; dbg_t[3] += tD - tC; dbg_t[4] += clock64() - tE; }
+      ccT = ccT_next;
     }
     cp_async_wait_all();
     if (dbg_on && tid == 0) { a.dbg[0] = dbg_t[0]; a.dbg[1] = clock64() - dbg_start; a.dbg[11] = dbg_t[1]; a.dbg[12] = dbg_t[2];
@@ -407,12 +414,14 @@ __global__ void __launch_bounds__(kThreads, 1) proj_gemm_kernel(const Args a) {
   } else if (warp == 8) {
     // ================================================================== bulk-copy producer (one thread)
     if (lane == 0) {
-      uint32_t it = 0;
-      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const uint32_t spt = 2u * (uint32_t)((a.kchunks + 1) / 2);
+      uint32_t T = 0, parBe = 0xFu;
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++T) {
         const int mt = (int)(tile / a.ntiles_n), nt = (int)(tile - (long long)mt * a.ntiles_n);
-        for (int kc = 0; kc < a.kchunks; ++kc, ++it) {
-          const int s = it % C::STAGES;
-          timed_wait(B_EMPTY(s), ((it / C::STAGES) & 1) ^ 1, 2);
+        for (int kc = 0; kc < a.kchunks; ++kc) {
+          const int s = (int)((T * spt + (uint32_t)kc) & 3u);
+          timed_wait(B_EMPTY(s), (parBe >> s) & 1u, 2);
+          parBe ^= 1u << s;
           tc::mbar_arrive_expect_tx(B_FULL(s), C::STAGE_BYTES);
           const float* src = a.wimg + ((size_t)nt * a.kchunks + kc) * (C::STAGE_BYTES / 4);
           tc::bulk_g2s(sbase + s * C::STAGE_BYTES, src, C::STAGE_BYTES, B_FULL(s));
@@ -421,22 +430,31 @@ __global__ void __launch_bounds__(kThreads, 1) proj_gemm_kernel(const Args a) {
       if (dbg_on) { a.dbg[4] = dbg_t[2]; a.dbg[5] = clock64() - dbg_start; }
     }
   } else {
-    // ================================================================== MMA issuer (one thread)
+    // ================================================================== MMA issuers (one thread each of warps 9 and 10)
+    // Chunk pairs alternate between the two accumulator buffers, and between the two issuing threads: a pair starts a
+    // fresh accumulation (first MMA overwrites), so the pairs are independent and no ordering is needed between the two
+    // threads' instruction streams; with chunk c on weight stage / A buffer c & 3 each issuer also owns its barriers
+    // (stages {0,1} or {2,3}), so their phases reach it in order.  While one thread sits in its barrier waits (~200 cycles each, three per chunk) the
+    // other one's MMAs keep the tensor pipe busy (measured with one issuer: 1800 cycles per chunk for 768 of MMA).
     if (lane == 0) {
       constexpr uint32_t idesc = tc::make_idesc(NT);
-      uint32_t it = 0, pp = 0;
+      const uint32_t me = (uint32_t)(warp - 9);
+      uint32_t pp = 0, T = 0, parAf = 0u, parBf = 0u;
       const int npairs = (a.kchunks + 1) / 2;
-      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const uint32_t spt = 2u * (uint32_t)npairs;
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++T) {
         for (int pr = 0; pr < npairs; ++pr, ++pp) {
+          if ((pp & 1u) != me) continue;
           const int dbuf = pp & 1;
           timed_wait(D_EMPTY(dbuf), ((pp >> 1) & 1) ^ 1, 3);       // the epilogue has drained this accumulator
           tc::fence_after_sync();
           const uint32_t dcol = tmem + dbuf * C::D_COLS;
           const int kc_end = min(a.kchunks, 2 * pr + 2);
-          for (int kc = 2 * pr; kc < kc_end; ++kc, ++it) {
-            const int s = it % C::STAGES, abuf = it & 1;
-            timed_wait(B_FULL(s), (it / C::STAGES) & 1, 4);
-            timed_wait(A_FULL(abuf), (it >> 1) & 1, 5);
+          for (int kc = 2 * pr; kc < kc_end; ++kc) {
+            const int s = (int)((T * spt + (uint32_t)kc) & 3u), abuf = s;
+            timed_wait(B_FULL(s), (parBf >> s) & 1u, 4);
+            timed_wait(A_FULL(abuf), (parAf >> s) & 1u, 5);
+            parBf ^= 1u << s; parAf ^= 1u << s;
             tc::fence_after_sync();
             const uint32_t bhi = sbase + s * C::STAGE_BYTES, blo = bhi + C::STAGE_BYTES / 2;
             const uint32_t ahi = tmem + C::A_COL0 + abuf * 64, alo = ahi + 32;
@@ -455,8 +473,8 @@ __global__ void __launch_bounds__(kThreads, 1) proj_gemm_kernel(const Args a) {
           tc::mma_commit(D_FULL(dbuf));
         }
       }
-      if (dbg_on) { a.dbg[6] = dbg_t[3]; a.dbg[7] = dbg_t[4]; a.dbg[8] = dbg_t[5]; a.dbg[9] = clock64() - dbg_start;
-                    a.dbg[10] = nchunks; }
+      if (dbg_on && me == 0) { a.dbg[6] = dbg_t[3]; a.dbg[7] = dbg_t[4]; a.dbg[8] = dbg_t[5]; a.dbg[9] = clock64() - dbg_start;
+                               a.dbg[10] = nchunks; }
     }
   }
 
@@ -507,6 +525,7 @@ struct Args {
   const float* X;       // (B, M, L)
   const float* Y;       // (B, L, N)
   const float* fir;     // (M, 3) or null
+  long long* dbg;       // optional per-role cycle counters of CTA 0 (tools/dbg_proj_timing.py), or null
   float* part;          // (splits, N, M) partial sums of the TRANSPOSED product
   int B, L, M, N;
   int chunks_per_b;     // ceil(L / 32)
@@ -548,6 +567,14 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a) {
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = *tmem_p;
+
+  const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0;
+  long long dbg_t[4] = {0, 0, 0, 0};
+  auto timed_wait = [&](uint32_t bar, uint32_t parity, int slot) {
+    if (dbg_on) { const long long t0 = clock64(); tc::mbar_wait_u(bar, parity); dbg_t[slot] += clock64() - t0; }
+    else tc::mbar_wait_u(bar, parity);
+  };
+  const long long dbg_start = clock64();
 
   // work item of this CTA
   const int split = blockIdx.x % a.splits;
@@ -604,7 +631,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a) {
     for (long long q = 0; q < nchunks; ++q) {
       cp_async_wait_group<kStg - 2>();
       pg::named_bar_sync(1, 128);
+      const long long tS = dbg_on ? clock64() : 0;
       if (q + kStg - 1 < nchunks) stage(q + kStg - 1); else cp_async_commit();
+      const long long tC = dbg_on ? clock64() : 0;
+      if (dbg_on) dbg_t[1] += tC - tS;
       const unsigned char* st = smem + kOffY + (size_t)(q % kStg) * kYStage;
       uint32_t hi[32], lo[32];
 #pragma unroll
@@ -616,7 +646,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a) {
       }
       const uint32_t it = (uint32_t)q;
       const int buf = it & 1;
-      tc::mbar_wait_u(A_EMPTY(buf), ((it >> 1) & 1) ^ 1);
+      if (dbg_on) dbg_t[2] += clock64() - tC;
+      timed_wait(A_EMPTY(buf), ((it >> 1) & 1) ^ 1, 0);
       tc::fence_after_sync();
       const uint32_t acol = kColA + buf * 64;
       tc::tmem_st32(lane_addr + acol, hi);
@@ -626,6 +657,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a) {
       tc::mbar_arrive(A_FULL(buf));
     }
     cp_async_wait_all();
+    if (dbg_on && tid == 0) { a.dbg[0] = dbg_t[0]; a.dbg[1] = dbg_t[1]; a.dbg[2] = dbg_t[2]; a.dbg[15] = nchunks;
+                              a.dbg[14] = clock64() - dbg_start; }
   } else if (warp < 8) {
     // ---------------------------------------------------------------- B side: X rows -> K-major hi / lo images
     const int t = tid - 128;
@@ -686,11 +719,14 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a) {
     for (long long q = 0; q < nchunks; ++q) {
       cp_async_wait_group<kStg - 2>();
       pg::named_bar_sync(2, 128);
+      const long long tS = dbg_on ? clock64() : 0;
       if (q + kStg - 1 < nchunks) stage(q + kStg - 1); else cp_async_commit();
+      if (dbg_on) dbg_t[1] += clock64() - tS;
       const unsigned char* st = smem + kOffX + (size_t)(q % kStg) * kXStage;
       const uint32_t it = (uint32_t)q;
       const int s = it & 1;
-      tc::mbar_wait_u(B_EMPTY(s), ((it >> 1) & 1) ^ 1);                 // the MMAs that read this image pair are done
+      timed_wait(B_EMPTY(s), ((it >> 1) & 1) ^ 1, 0);                   // the MMAs that read this image pair are done
+      const long long tV = dbg_on ? clock64() : 0;
       unsigned char* hi_img = smem + kOffImg + (size_t)s * 2 * kImg;
       unsigned char* lo_img = hi_img + kImg;
 #pragma unroll
@@ -717,8 +753,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a) {
       }
       tc::fence_async_smem();
       tc::mbar_arrive(B_FULL(s));
+      if (dbg_on) dbg_t[2] += clock64() - tV;
     }
     cp_async_wait_all();
+    if (dbg_on && t == 0) { a.dbg[3] = dbg_t[0]; a.dbg[4] = dbg_t[1]; a.dbg[5] = dbg_t[2]; }
   } else {
     // ---------------------------------------------------------------- MMA issuer
     if (warp == 8 && lane == 0) {
@@ -728,11 +766,11 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a) {
         const int s = it & 1;
         const uint32_t seg = it / kSeg, sb = seg & 1;
         if (it % kSeg == 0) {                                           // new segment: its main accumulator must be drained
-          tc::mbar_wait_u(DM_EMPTY(sb), ((seg >> 1) & 1) ^ 1);
+          timed_wait(DM_EMPTY(sb), ((seg >> 1) & 1) ^ 1, 0);
           tc::fence_after_sync();
         }
-        tc::mbar_wait_u(B_FULL(s), (it >> 1) & 1);
-        tc::mbar_wait_u(A_FULL(s), (it >> 1) & 1);
+        timed_wait(B_FULL(s), (it >> 1) & 1, 1);
+        timed_wait(A_FULL(s), (it >> 1) & 1, 2);
         tc::fence_after_sync();
         const uint32_t bhi = sbase + kOffImg + s * 2 * kImg, blo = bhi + kImg;
         const uint32_t ahi = tmem + kColA + s * 64, alo = ahi + 32;
@@ -752,6 +790,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a) {
         if (it % kSeg == kSeg - 1 || q + 1 == nchunks) tc::mma_commit(DM_FULL(sb));
       }
       if (nchunks > 0) tc::mma_commit(DC_FULL);
+      if (dbg_on) { a.dbg[6] = dbg_t[0]; a.dbg[7] = dbg_t[1]; a.dbg[8] = dbg_t[2]; a.dbg[9] = clock64() - dbg_start; }
     }
   }
   if (warp >= 9) {
@@ -794,16 +833,19 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a) {
     } else {
       for (uint32_t seg = 0; seg < nseg; ++seg) {
         const int sb = seg & 1;
-        tc::mbar_wait_u(DM_FULL(sb), (seg >> 1) & 1);
+        timed_wait(DM_FULL(sb), (seg >> 1) & 1, 0);
         tc::fence_after_sync();
+        const long long tD = dbg_on ? clock64() : 0;
         add_cols(sb * 128, seg == 0);
         tc::fence_before_sync();
         tc::mbar_arrive(DM_EMPTY(sb));
+        if (dbg_on) dbg_t[1] += clock64() - tD;
       }
       tc::mbar_wait_u(DC_FULL, 0);
       tc::fence_after_sync();
       add_cols(kColDC, false);
       tc::fence_before_sync();
+      if (dbg_on && warp == 9 && lane == 0) { a.dbg[10] = dbg_t[0]; a.dbg[11] = dbg_t[1]; }
     }
   }
   tc::fence_before_sync();
