@@ -1,4 +1,6 @@
 // Launchers of the tcgen05 projection GEMMs (proj_gemm.cuh).
+#include <cstring>
+
 #include "launch.h"
 #include "proj_gemm.cuh"
 
@@ -11,9 +13,47 @@ size_t proj_wimg_bytes(int N, int K) {
   return pg::wimg_floats(N, K, NT) * sizeof(float);
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no libcuda link dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// fp32 matrix (rows x cols, row pitch = cols) -> tensor map with box (box_cols x box_rows)
+static bool make_tmap(CUtensorMap* m, const float* base, unsigned long long rows, unsigned long long cols, unsigned box_cols,
+                      unsigned box_rows, bool swizzle128) {
+  EncodeTiledFn f = encode_tiled();
+  if (!f) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * sizeof(float)};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return f(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int NT, int ACT, int OUT>
-static cudaError_t go(const pg::Args& a, int sms, cudaStream_t s) {
+static cudaError_t go(pg::Args a, int sms, cudaStream_t s) {
   auto kern = pg::proj_gemm_kernel<NT, ACT, OUT>;
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (a.vec) {
+    const bool ok = (ACT == pg::ACT_ROW)
+        ? make_tmap(&tmap, a.act, (unsigned long long)a.B * a.L, (unsigned long long)a.K, 32, 128, true)
+        : make_tmap(&tmap, a.act, (unsigned long long)a.B * a.K, (unsigned long long)a.L, 132, 32, false);
+    if (!ok) a.vec = 0;                    // no driver entry point / unencodable shape: lanes stage the tiles instead
+  }
   const size_t smem = pg::Cfg<NT>::SMEM + (a.fir ? (size_t)a.K * 12 : 0);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -21,7 +61,7 @@ static cudaError_t go(const pg::Args& a, int sms, cudaStream_t s) {
   const long long ntiles = (long long)a.B * a.mtiles_per_b * a.ntiles_n;
   const int grid = (int)(ntiles < sms ? ntiles : sms);
   prof_begin(K_PROJ_GEMM, s);
-  kern<<<grid, pg::kThreads, smem, s>>>(a);
+  kern<<<grid, pg::kThreads, smem, s>>>(a, tmap);
   prof_end(K_PROJ_GEMM, s);
   return cudaGetLastError();
 }
@@ -54,8 +94,10 @@ cudaError_t launch_proj_gemm(const float* act, int act_layout, const float* W, i
   a.act = act; a.wimg = wimg; a.out = out; a.bias = bias; a.fir = fir;
   a.dbg = g_proj_dbg;
   a.B = B; a.L = L; a.K = K; a.N = N; a.l0 = l0; a.ln = ln;
+  // TMA needs 16-byte aligned rows (global stride a multiple of 16 bytes) and, for the channel-major box, a 16-byte
+  // aligned first position
   if (act_layout == pg::ACT_ROW) a.vec = (K % 4 == 0);
-  else a.vec = (L % 4 == 0) && (l0 % 4 == 0) && (ln % 4 == 0);
+  else a.vec = (L % 4 == 0) && (l0 % 4 == 0);
   a.kchunks = (K + pg::kKC - 1) / pg::kKC;
   a.ntiles_n = (N + NT - 1) / NT;
   a.mtiles_per_b = (ln + 127) / 128;

@@ -7,8 +7,8 @@
 // warp-specialised kernel (proj_gemm_kernel):
 //
 //   tile      128 positions (UMMA M = 128, one TMEM lane per position) x NT outputs, K streamed in chunks of 32
-//   A operand the activation chunk: global -> shared-memory ring by cp.async (four chunks in flight, no registers held
-//             across the DRAM latency) -> registers -> (hi, lo) tf32 split -> TENSOR MEMORY (tcgen05.st).  The MMAs
+//   A operand the activation chunk: global -> shared-memory ring by TMA bulk copies issued by a producer warp (one copy per
+//             row of the chunk, four chunks in flight) -> registers -> (hi, lo) tf32 split -> TENSOR MEMORY (tcgen05.st).  The MMAs
 //             read A from TMEM: the shared-memory port is the scarce resource of a tf32 MMA (an SS-mode M128 N256 K8
 //             instruction reads 12 KB per 128 cycles), so only B goes through it.
 //   B operand the weights, pre-split once per call into hi / lo images in the canonical no-swizzle K-major
@@ -21,14 +21,15 @@
 //             error of cuBLASLt's BF16x9 on y at L = 2^20, the 2^20-position weight gradients lost four digits.
 //   3xTF32    x = hi + lo, hi = rna_tf32(x), lo = rna_tf32(x - hi);  D += Ahi Bhi + Alo Bhi + Ahi Blo   (lo*lo < 2^-22)
 //
-// Warp roles (352 threads): warps 0-3 stage + convert (thread = position), warps 4-7 epilogue (thread = position),
-// warp 8 lane 0 bulk-copy producer, warps 9 and 10 lane 0 MMA issuers (alternate chunk pairs).
+// Warp roles: see the comment above proj_gemm_kernel.
 //
 // Optional fused prologue (FIR): the activation is ds (B, C, L) and the GEMM consumes dp = transposed 3-tap depthwise
 // filter of ds (dp[t] = w2 ds[t] + w1 ds[t+1] + w0 ds[t+2], hyena.py:363-369 backward), so dp never exists in HBM.
 //
 // Weight gradients (wgrad_kernel) at the end of the file.
 #pragma once
+#include <cuda.h>      // CUtensorMap (types only: the encode function is looked up at run time, no libcuda link)
+
 #include "common.cuh"
 #include "tc_prims.cuh"
 
@@ -36,8 +37,7 @@ namespace hy {
 namespace pg {
 
 constexpr int kKC = 32;                 // K chunk (one chunk = 4 MMAs of K = 8 per product)
-constexpr int kThreads = 352;          // 11 warps: 4 convert, 4 epilogue, 1 bulk-copy producer, 2 MMA issuers
-constexpr int kAStages = 4;             // activation chunks in flight
+constexpr int kThreads = 480;          // 15 warps: 4 convert, 8 epilogue, 1 TMA producer, 2 MMA issuers
 constexpr uint32_t kSBO = 1024, kLBO = 128;
 constexpr uint32_t kAPitchCh = 132 * 4; // ACT_CH staging row: 128 positions + one look-ahead quad (fused FIR)
 constexpr uint32_t kAStageBytes = 32 * kAPitchCh;      // 16.5 KB (>= the 16 KB an ACT_ROW tile needs)
@@ -61,7 +61,7 @@ struct Args {
   int kchunks;           // ceil(K / 32)
   int ntiles_n;          // ceil(N / NT)
   int mtiles_per_b;      // ceil(ln / 128)
-  int vec;               // 1: 16-byte cp.async staging is legal (alignment / divisibility checked on the host)
+  int vec;               // 1: the activation qualifies for TMA (16-byte aligned rows): `tmap` is valid
   long long* dbg;        // optional (tools/dbg_proj_timing.py): per-role wait / work cycle counters of CTA 0, or null
 };
 
@@ -92,19 +92,26 @@ __host__ __device__ constexpr size_t wimg_floats(int N, int K, int NT) {
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
+// Activation staging slot (17 KB, 1024-byte aligned):
+//   ACT_ROW  128 rows x 32 floats (128-byte rows), 16-byte pieces XOR-swizzled by the row (= TMA SWIZZLE_128B): LDS.128 of
+//            32 different rows at the same logical piece is bank-conflict free
+//   ACT_CH   32 channel rows x 132 floats (128 positions + 4 look-ahead samples for the fused FIR), dense
+constexpr uint32_t kSStageBytes = 17408;
+static_assert(kSStageBytes >= 32 * kAPitchCh && kSStageBytes >= 128 * 128 && kSStageBytes % 1024 == 0, "staging slot");
+
 template <int NT> struct Cfg {
-  static constexpr int STAGES = 4;                                     // weight stages (the weights come from L2)
+  static constexpr int STAGES = 4;                                     // weight stages = A buffers = staging slots
   static constexpr uint32_t STAGE_BYTES = 2u * NT * kKC * 4u;          // hi + lo image of one K chunk
   static constexpr uint32_t D_COLS = NT;                               // per accumulator buffer
   static constexpr uint32_t A_COL0 = 2 * NT;                           // A buffers after the two accumulators
   static constexpr uint32_t TMEM_COLS = 512;
   static constexpr size_t OFF_A = (size_t)STAGES * STAGE_BYTES;        // activation staging ring
-  static constexpr size_t OFF_BAR = OFF_A + (size_t)kAStages * kAStageBytes;
+  static constexpr size_t OFF_BAR = OFF_A + (size_t)STAGES * kSStageBytes;
   static constexpr size_t OFF_FIR = OFF_BAR + 256;
   static constexpr size_t SMEM = OFF_FIR;                              // + 12 K bytes of taps when the FIR is fused
   static_assert(2 * NT + 4 * 64 <= 512, "two accumulators and four A (hi, lo) chunk buffers must fit tensor memory");
-  static_assert(NT == 128, "the epilogue keeps NT partial sums per thread in registers");
-  static_assert(STAGES == 4, "chunk c uses weight stage and A buffer c & 3: pair p (chunks 2p, 2p+1) then owns stages "
+  static_assert(NT == 128, "the epilogue keeps NT / 2 partial sums per thread in registers");
+  static_assert(STAGES == 4, "slot c uses weight stage / staging slot / A buffer c & 3: a chunk pair then owns stages "
                              "{0,1} or {2,3}, i.e. each of the two MMA issuers sees its barriers' phases in order");
 };
 
@@ -112,22 +119,30 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Warp roles (480 threads):
+//   warps 0-3    convert: staged activation chunk -> registers (-> fused FIR) -> (hi, lo) split -> tensor memory
+//   warps 4-7    epilogue, output columns [0, 64)   } thread = position; drain every chunk pair into registers,
+//   warps 11-14  epilogue, output columns [64, 128) } store the tile at the end
+//   warp 8       producer: TMA bulk copies of the weight images (lane 0) and of the activation rows (all lanes)
+//   warps 9, 10  MMA issuers (lane 0 each), alternate chunk pairs
 template <int NT, int ACT, int OUT>
-__global__ void __launch_bounds__(kThreads, 1) proj_gemm_kernel(const Args a) {
+__global__ void __launch_bounds__(kThreads, 1) proj_gemm_kernel(const Args a, const __grid_constant__ CUtensorMap tmap) {
   using C = Cfg<NT>;
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
-  // barrier map: b_full[S] b_empty[S] a_full[4] a_empty[4] d_full[2] d_empty[2]
-  uint32_t* tmem_p = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 12);
+  // barrier map: b_full[4] b_empty[4] a_full[4] a_empty[4] s_full[4] s_empty[4] d_full[2] d_empty[2]
+  uint32_t* tmem_p = reinterpret_cast<uint32_t*>(bars + 28);
   float* fir_s = reinterpret_cast<float*>(smem + C::OFF_FIR);     // (K, 3) taps, FIR only
   const uint32_t sbase = tc::smem_u32(smem);
   const uint32_t bar0 = tc::smem_u32(bars);
   auto B_FULL = [&](int s) { return bar0 + 8u * s; };
-  auto B_EMPTY = [&](int s) { return bar0 + 8u * (C::STAGES + s); };
-  auto A_FULL = [&](int j) { return bar0 + 8u * (2 * C::STAGES + j); };
-  auto A_EMPTY = [&](int j) { return bar0 + 8u * (2 * C::STAGES + 4 + j); };
-  auto D_FULL = [&](int j) { return bar0 + 8u * (2 * C::STAGES + 8 + j); };
-  auto D_EMPTY = [&](int j) { return bar0 + 8u * (2 * C::STAGES + 10 + j); };
+  auto B_EMPTY = [&](int s) { return bar0 + 8u * (4 + s); };
+  auto A_FULL = [&](int j) { return bar0 + 8u * (8 + j); };
+  auto A_EMPTY = [&](int j) { return bar0 + 8u * (12 + j); };
+  auto S_FULL = [&](int j) { return bar0 + 8u * (16 + j); };
+  auto S_EMPTY = [&](int j) { return bar0 + 8u * (20 + j); };
+  auto D_FULL = [&](int j) { return bar0 + 8u * (24 + j); };
+  auto D_EMPTY = [&](int j) { return bar0 + 8u * (26 + j); };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool use_fir = (ACT == ACT_CH) && a.fir != nullptr;
@@ -139,18 +154,21 @@ __global__ void __launch_bounds__(kThreads, 1) proj_gemm_kernel(const Args a) {
   if (use_fir)
     for (int i = tid; i < 3 * a.K; i += kThreads) fir_s[i] = __ldg(a.fir + i);
   if (tid == 0) {
-    for (int s = 0; s < C::STAGES; ++s) { tc::mbar_init(B_FULL(s), 1); tc::mbar_init(B_EMPTY(s), 1); }
-    for (int j = 0; j < 4; ++j) { tc::mbar_init(A_FULL(j), 128); tc::mbar_init(A_EMPTY(j), 1); }
-    for (int j = 0; j < 2; ++j) { tc::mbar_init(D_FULL(j), 1); tc::mbar_init(D_EMPTY(j), 128); }
+    for (int s = 0; s < 4; ++s) {
+      tc::mbar_init(B_FULL(s), 1); tc::mbar_init(B_EMPTY(s), 1);
+      tc::mbar_init(A_FULL(s), 128); tc::mbar_init(A_EMPTY(s), 1);
+      tc::mbar_init(S_FULL(s), 1); tc::mbar_init(S_EMPTY(s), 128);
+    }
+    for (int j = 0; j < 2; ++j) { tc::mbar_init(D_FULL(j), 1); tc::mbar_init(D_EMPTY(j), 256); }
   }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = *tmem_p;
 
-  // debug timing: cycles spent in a barrier wait, accumulated per role (lane 0 of each role's first warp, CTA 0)
+  // debug timing: cycles spent in barrier waits, per role (CTA 0), see tools/dbg_proj_timing.py
   const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0;
-  long long dbg_t[6] = {0, 0, 0, 0, 0, 0};
+  long long dbg_t[4] = {0, 0, 0, 0};
   auto timed_wait = [&](uint32_t bar, uint32_t parity, int slot) {
     if (dbg_on) {
       const long long t0 = clock64();
@@ -163,199 +181,204 @@ __global__ void __launch_bounds__(kThreads, 1) proj_gemm_kernel(const Args a) {
   const long long dbg_start = clock64();
 
   const int mtiles = a.B * a.mtiles_per_b;
-  const long long ntiles = (long long)mtiles * a.ntiles_n;
-  const int my_tiles = (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);      // tiles of this CTA (>= 1)
-  const long long nchunks = (long long)my_tiles * a.kchunks;                         // chunks of this CTA
+  const int ntiles = mtiles * a.ntiles_n;
+  const int npairs = (a.kchunks + 1) / 2;
+  // slot numbering shared by all roles: tile ordinal T of this CTA owns slots [T * spt, (T + 1) * spt), spt = 2 * npairs
+  // (even: with an odd chunk count the last slot of a tile stays unused); slot -> stage / staging slot / A buffer slot & 3
+  const uint32_t spt = 2u * (uint32_t)npairs;
+  const int lend = a.l0 + a.ln;
+  auto tile_pos = [&](int tile, int& b, int& lt, int& nt) {
+    const int mt = tile / a.ntiles_n;
+    nt = tile - mt * a.ntiles_n;
+    b = mt / a.mtiles_per_b;
+    lt = a.l0 + (mt - b * a.mtiles_per_b) * 128;
+  };
 
   if (warp < 4) {
-    // ================================================================== stage + convert: thread = position of the tile
+    // ================================================================== converters: thread = position of the tile
     const int row = tid;                                           // 0..127 == TMEM lane
     const uint32_t lane_addr = tmem + ((uint32_t)(32 * warp) << 16);
-    unsigned char* ring = smem + C::OFF_A;
-
-    // Cursors over this CTA's (tile, chunk) list, advanced incrementally (no divisions in the loop): one for the chunk
-    // being staged (kAStages - 1 ahead), one for the chunk being converted.
-    struct Cur { int tile, kc, b, lt; };
-    auto cur_set = [&](Cur& c, int tile) {
-      c.tile = tile; c.kc = 0;
-      const int mt = tile / a.ntiles_n;
-      c.b = mt / a.mtiles_per_b;
-      c.lt = a.l0 + (mt - c.b * a.mtiles_per_b) * 128;
-    };
-    auto cur_next = [&](Cur& c) {
-      if (++c.kc == a.kchunks) cur_set(c, c.tile + (int)gridDim.x);
-    };
-    const int lend = a.l0 + a.ln;
-    // per-thread constants of the staging pattern
-    //   ACT_ROW: pieces (row (tid >> 3) + 16 i, 16-byte column tid & 7), i < 8: a warp copies four whole 128-byte rows
-    //   ACT_CH : pieces (channel (tid >> 5) + 4 i, quad tid & 31), i < 8: a warp copies 512 contiguous bytes of one channel
-    const int r0 = tid >> 3, c8 = tid & 7;
-    const int j0 = tid >> 5, q32 = tid & 31;
-    const uint32_t dst_row0 = (uint32_t)(r0 * 128 + ((c8 ^ (r0 & 7)) << 4));
-    const uint32_t dst_ch0 = (uint32_t)(j0 * kAPitchCh + q32 * 16);
-
-    // fill staging slot `slot` with the chunk at cursor c (asynchronously when the layout allows 16-byte copies)
-    auto stage = [&](const Cur& c, int slot) {
-      unsigned char* st = ring + (size_t)slot * kAStageBytes;
-      const int k0 = c.kc * kKC;
-      if constexpr (ACT == ACT_ROW) {
-        const float* base = a.act + ((size_t)c.b * a.L + c.lt) * a.K + k0;
-        if (a.vec && k0 + kKC <= a.K) {
-          if (c.lt + 128 <= lend) {                                 // interior tile: no predicates
-            const float* src = base + (size_t)r0 * a.K + 4 * c8;
+    uint32_t T = 0, parSf = 0u, parAe = 0xFu;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++T) {
+      for (int kc = 0; kc < a.kchunks; ++kc) {
+        const int s = (int)((T * spt + (uint32_t)kc) & 3u);
+        timed_wait(S_FULL(s), (parSf >> s) & 1u, 0);              // the producer's copies of this chunk have landed
+        parSf ^= 1u << s;
+        const unsigned char* st = smem + C::OFF_A + (size_t)s * kSStageBytes;
+        float x[kKC];
+        if constexpr (ACT == ACT_ROW) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) cp_async16(st + dst_row0 + i * 2048, src + (size_t)i * 16 * a.K, true);
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = *reinterpret_cast<const float4*>(st + row * 128 + ((c ^ (row & 7)) << 4));
+            x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+          }
+        } else {
+          if (!use_fir) {
+#pragma unroll
+            for (int j = 0; j < kKC; ++j) x[j] = *reinterpret_cast<const float*>(st + j * kAPitchCh + row * 4);
           } else {
+            // dp[t] = w2 ds[t] + w1 ds[t+1] + w0 ds[t+2]; ds beyond the tensor end is staged as zero, a position beyond
+            // the processed range produces a value nobody stores; channels >= K are staged as zero
+            const int k0 = kc * kKC;
+            const bool kfull = k0 + kKC <= a.K;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const bool ok = c.lt + r0 + 16 * i < lend;
-              cp_async16(st + dst_row0 + i * 2048, base + (ok ? (size_t)(r0 + 16 * i) * a.K + 4 * c8 : 0), ok);
+            for (int j = 0; j < kKC; ++j) {
+              const float* sp = reinterpret_cast<const float*>(st + j * kAPitchCh) + row;
+              const float* w = fir_s + 3 * ((kfull || k0 + j < a.K) ? k0 + j : 0);
+              x[j] = fmaf(w[2], sp[0], fmaf(w[1], sp[1], w[0] * sp[2]));
             }
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = r0 + 16 * i;
-            const bool rv = c.lt + r < lend;
-            const float* src = base + (size_t)(rv ? r : 0) * a.K + 4 * c8;
-            float4 v;
-            v.x = (rv && k0 + 4 * c8 + 0 < a.K) ? __ldg(src + 0) : 0.f;
-            v.y = (rv && k0 + 4 * c8 + 1 < a.K) ? __ldg(src + 1) : 0.f;
-            v.z = (rv && k0 + 4 * c8 + 2 < a.K) ? __ldg(src + 2) : 0.f;
-            v.w = (rv && k0 + 4 * c8 + 3 < a.K) ? __ldg(src + 3) : 0.f;
-            *reinterpret_cast<float4*>(st + dst_row0 + i * 2048) = v;
-          }
         }
-      } else {
-        const float* base = a.act + ((size_t)c.b * a.K + k0) * a.L + c.lt;
-        const bool interior = (k0 + kKC <= a.K) && (c.lt + 128 <= lend) && (!use_fir || c.lt + 132 <= a.L);
-        if (a.vec && interior) {
-          const float* src = base + (size_t)j0 * a.L + 4 * q32;
+        tc::mbar_arrive(S_EMPTY(s));                               // staging slot read: the producer may refill it
+        uint32_t hi[kKC], lo[kKC];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) cp_async16(st + dst_ch0 + i * 4 * kAPitchCh, src + (size_t)i * 4 * a.L, true);
-          if (use_fir && tid < 32) cp_async16(st + tid * kAPitchCh + 512, base + (size_t)tid * a.L + 128, true);
-        } else {
-          // edge tile / ragged K / unaligned tensor: per-piece bounds; the 128 tile positions stop at the processed range,
-          // the look-ahead quad (fused FIR) at the end of the tensor
-          auto piece = [&](int j, int qd) {
-            const int l = c.lt + 4 * qd;
-            const int lim = (qd == 32) ? a.L : lend;
-            const bool kv = k0 + j < a.K;
-            const float* src = a.act + ((size_t)c.b * a.K + (kv ? k0 + j : 0)) * a.L;
-            unsigned char* dst = st + j * kAPitchCh + qd * 16;
-            if (a.vec) {
-              const bool ok = kv && (l + 4 <= lim);
-              cp_async16(dst, src + (ok ? l : 0), ok);
+        for (int j = 0; j < kKC; ++j) {
+          float hh, lw;
+          tc::split_tf32(x[j], hh, lw);
+          hi[j] = __float_as_uint(hh); lo[j] = __float_as_uint(lw);
+        }
+        timed_wait(A_EMPTY(s), (parAe >> s) & 1u, 1);             // MMAs of the previous use of this A buffer are done
+        parAe ^= 1u << s;
+        tc::fence_after_sync();
+        const uint32_t acol = C::A_COL0 + s * 64;
+        tc::tmem_st32(lane_addr + acol, hi);
+        tc::tmem_st32(lane_addr + acol + 32, lo);
+        tc::tmem_wait_st();
+        tc::fence_before_sync();
+        tc::mbar_arrive(A_FULL(s));
+      }
+    }
+    if (dbg_on && tid == 0) { a.dbg[0] = dbg_t[0]; a.dbg[1] = dbg_t[1]; a.dbg[2] = clock64() - dbg_start; }
+  } else if (warp == 8) {
+    // ================================================================== producer: weight images + activation tiles (TMA)
+    // One thread issues, per chunk, one bulk copy of the weight stage and ONE tiled TMA copy of the activation tile
+    // (tensor map: box 32 k x 128 positions, 128-byte swizzle, for a row-major activation; box 132 positions x 32
+    // channels for a channel-major one).  Out-of-range coordinates are zero-filled by the copy engine (end of the tensor:
+    // exactly the zero padding the fused FIR needs; K tail).  Activations that do not qualify for TMA (rows not 16-byte
+    // aligned) are staged by the 32 lanes with plain loads and stores instead.
+    if (lane == 0 && a.vec) tc::tma_prefetch_desc(&tmap);
+    uint32_t T = 0, parBe = 0xFu, parSe = 0xFu;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++T) {
+      int b, lt, nt;
+      tile_pos(tile, b, lt, nt);
+      for (int kc = 0; kc < a.kchunks; ++kc) {
+        const int s = (int)((T * spt + (uint32_t)kc) & 3u);
+        const int k0 = kc * kKC;
+        const uint32_t st_u = sbase + (uint32_t)C::OFF_A + (uint32_t)s * kSStageBytes;
+        if (lane == 0) {
+          timed_wait(B_EMPTY(s), (parBe >> s) & 1u, 0);
+          tc::mbar_arrive_expect_tx(B_FULL(s), C::STAGE_BYTES);
+          const float* src = a.wimg + ((size_t)nt * a.kchunks + kc) * (C::STAGE_BYTES / 4);
+          tc::bulk_g2s(sbase + s * C::STAGE_BYTES, src, C::STAGE_BYTES, B_FULL(s));
+          timed_wait(S_EMPTY(s), (parSe >> s) & 1u, 1);
+          if (a.vec) {
+            if constexpr (ACT == ACT_ROW) {
+              tc::mbar_arrive_expect_tx(S_FULL(s), 128u * 128u);
+              tc::tma_load_2d(st_u, &tmap, k0, b * a.L + lt, S_FULL(s));
             } else {
-              float4 v;
-              v.x = (kv && l + 0 < lim) ? __ldg(src + l + 0) : 0.f;
-              v.y = (kv && l + 1 < lim) ? __ldg(src + l + 1) : 0.f;
-              v.z = (kv && l + 2 < lim) ? __ldg(src + l + 2) : 0.f;
-              v.w = (kv && l + 3 < lim) ? __ldg(src + l + 3) : 0.f;
-              *reinterpret_cast<float4*>(dst) = v;
+              tc::mbar_arrive_expect_tx(S_FULL(s), 32u * kAPitchCh);
+              tc::tma_load_2d(st_u, &tmap, lt, b * a.K + k0, S_FULL(s));
             }
-          };
-#pragma unroll
-          for (int i = 0; i < 8; ++i) piece(j0 + 4 * i, q32);
-          if (use_fir && tid < 32) piece(tid, 32);
-        }
-      }
-      cp_async_commit();
-    };
-
-    const uint32_t spt = 2u * (uint32_t)((a.kchunks + 1) / 2);
-    uint32_t ccT = 0, ccT_next = 0, parAe = 0xFu;                   // tile ordinal of the conversion cursor; wait parities
-    Cur cs, cc;                                                     // staging cursor, conversion cursor
-    cur_set(cs, (int)blockIdx.x);
-    cc = cs;
-    int q_staged = 0;
-    for (; q_staged < kAStages - 1; ++q_staged) {
-      if (q_staged < nchunks) { stage(cs, q_staged % kAStages); cur_next(cs); } else cp_async_commit();
-    }
-    for (int q = 0; q < (int)nchunks; ++q) {
-      long long tA = dbg_on ? clock64() : 0;
-      cp_async_wait_group<kAStages - 2>();                         // chunk q has landed (this thread's pieces)
-      named_bar_sync(1, 128);                                      // ... and everybody else's; slot (q-1) % S is free
-      long long tB = dbg_on ? clock64() : 0;
-      if (q_staged < nchunks) { stage(cs, q_staged % kAStages); cur_next(cs); } else cp_async_commit();
-      ++q_staged;
-      long long tC = dbg_on ? clock64() : 0;
-      const unsigned char* st = ring + (size_t)(q % kAStages) * kAStageBytes;
-      float x[kKC];
-      if constexpr (ACT == ACT_ROW) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 v = *reinterpret_cast<const float4*>(st + row * 128 + ((c ^ (row & 7)) << 4));
-          x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
-        }
-      } else {
-        if (!use_fir) {
-#pragma unroll
-          for (int j = 0; j < kKC; ++j) x[j] = *reinterpret_cast<const float*>(st + j * kAPitchCh + row * 4);
-        } else {
-          // dp[t] = w2 ds[t] + w1 ds[t+1] + w0 ds[t+2]; ds beyond the tensor end is zero (staged as zero), a position
-          // beyond the processed range produces a value nobody stores; taps of channels >= K are read as channel 0's and
-          // multiply staged zeros
-          const int k0 = cc.kc * kKC;
-          const bool kfull = k0 + kKC <= a.K;
-#pragma unroll
-          for (int j = 0; j < kKC; ++j) {
-            const float* sp = reinterpret_cast<const float*>(st + j * kAPitchCh) + row;
-            const float* w = fir_s + 3 * ((kfull || k0 + j < a.K) ? k0 + j : 0);
-            x[j] = fmaf(w[2], sp[0], fmaf(w[1], sp[1], w[0] * sp[2]));
           }
         }
-      }
-      const int cc_kc = cc.kc;
-      { const int t0 = cc.tile; cur_next(cc); if (cc.tile != t0) ++ccT_next; }
-      uint32_t hi[kKC], lo[kKC];
+        parBe ^= 1u << s; parSe ^= 1u << s;
+        if (!a.vec) {
+          __syncwarp();
+          unsigned char* st = smem + C::OFF_A + (size_t)s * kSStageBytes;
+          if constexpr (ACT == ACT_ROW) {
+#pragma unroll 1
+            for (int i = 0; i < 4; ++i) {
+              const int r = lane + 32 * i, l = lt + r;
+              const float* src = a.act + ((size_t)b * a.L + (l < lend ? l : 0)) * a.K + k0;
 #pragma unroll
-      for (int j = 0; j < kKC; ++j) {
-        float hh, lw;
-        tc::split_tf32(x[j], hh, lw);
-        hi[j] = __float_as_uint(hh); lo[j] = __float_as_uint(lw);
+              for (int c = 0; c < 8; ++c) {
+                float4 v;
+                v.x = (l < lend && k0 + 4 * c + 0 < a.K) ? __ldg(src + 4 * c + 0) : 0.f;
+                v.y = (l < lend && k0 + 4 * c + 1 < a.K) ? __ldg(src + 4 * c + 1) : 0.f;
+                v.z = (l < lend && k0 + 4 * c + 2 < a.K) ? __ldg(src + 4 * c + 2) : 0.f;
+                v.w = (l < lend && k0 + 4 * c + 3 < a.K) ? __ldg(src + 4 * c + 3) : 0.f;
+                *reinterpret_cast<float4*>(st + r * 128 + ((c ^ (r & 7)) << 4)) = v;
+              }
+            }
+          } else {
+            const int j = lane;
+            const bool kv = k0 + j < a.K;
+            const float* src = a.act + ((size_t)b * a.K + (kv ? k0 + j : 0)) * a.L + lt;
+            float* dst = reinterpret_cast<float*>(st + j * kAPitchCh);
+            for (int e = 0; e < 132; ++e) dst[e] = (kv && lt + e < a.L) ? __ldg(src + e) : 0.f;
+          }
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(S_FULL(s));
+        }
       }
-      // slot numbering shared by all roles: tile T of this CTA owns slots [T * spt, (T+1) * spt), spt = 2 * pairs per tile
-      // (even: with an odd number of chunks the last slot of a tile stays unused); slot -> A buffer / weight stage slot & 3
-      const uint32_t it = ccT * spt + (uint32_t)cc_kc;
-      const int buf = it & 3;
-      long long tD = dbg_on ? clock64() : 0;
-      timed_wait(A_EMPTY(buf), (parAe >> buf) & 1u, 0);           // MMAs of the previous use of this buffer are done
-      parAe ^= 1u << buf;
-      tc::fence_after_sync();
-      long long tE = dbg_on ? clock64() : 0;
-      const uint32_t acol = C::A_COL0 + buf * 64;
-      tc::tmem_st32(lane_addr + acol, hi);
-      tc::tmem_st32(lane_addr + acol + 32, lo);
-      tc::tmem_wait_st();
-      tc::fence_before_sync();
-      tc::mbar_arrive(A_FULL(buf));
-      if (dbg_on) { dbg_t[1] += tB - tA; dbg_t[2] += tC - tB; dbg_t[3] += tD - tC; dbg_t[4] += clock64() - tE; }
-      ccT = ccT_next;
     }
-    cp_async_wait_all();
-    if (dbg_on && tid == 0) { a.dbg[0] = dbg_t[0]; a.dbg[1] = clock64() - dbg_start; a.dbg[11] = dbg_t[1]; a.dbg[12] = dbg_t[2];
-                              a.dbg[13] = dbg_t[3]; a.dbg[14] = dbg_t[4]; }
-  } else if (warp < 8) {
-    // ================================================================== epilogue: thread = position of the tile
-    const int w4 = warp - 4, row = 32 * w4 + lane;
-    const uint32_t lane_addr = tmem + ((uint32_t)(32 * w4) << 16);
-    uint32_t pp = 0;                                               // chunk-pair counter over the CTA's whole work list
-    const int npairs = (a.kchunks + 1) / 2;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int mt = (int)(tile / a.ntiles_n), nt = (int)(tile - (long long)mt * a.ntiles_n);
-      const int b = mt / a.mtiles_per_b, l = a.l0 + (mt - b * a.mtiles_per_b) * 128 + row;
-      const bool pv = l < a.l0 + a.ln;
-      float acc[NT];
+    if (dbg_on && lane == 0) { a.dbg[3] = dbg_t[0]; a.dbg[4] = dbg_t[1]; }
+  } else if (warp == 9 || warp == 10) {
+    // ================================================================== MMA issuers (one thread each of warps 9 and 10)
+    // Chunk pairs alternate between the two accumulator buffers, and between the two issuing threads: a pair starts a
+    // fresh accumulation (first MMA overwrites), so the pairs are independent and no ordering is needed between the two
+    // threads' instruction streams; with slot c on stage / A buffer c & 3 each issuer also owns its barriers (stages
+    // {0,1} or {2,3}), so their phases reach it in order.  While one thread sits in its barrier waits (~200 cycles each)
+    // the other one's MMAs keep the tensor pipe busy (measured with one issuer: 1800 cycles per chunk for 768 of MMA).
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc(NT);
+      const uint32_t me = (uint32_t)(warp - 9);
+      uint32_t pp = 0, T = 0, parAf = 0u, parBf = 0u;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++T) {
+        for (int pr = 0; pr < npairs; ++pr, ++pp) {
+          if ((pp & 1u) != me) continue;
+          const int dbuf = pp & 1;
+          timed_wait(D_EMPTY(dbuf), ((pp >> 1) & 1) ^ 1, 0);       // the epilogue has drained this accumulator
+          tc::fence_after_sync();
+          const uint32_t dcol = tmem + dbuf * C::D_COLS;
+          const int kc_end = min(a.kchunks, 2 * pr + 2);
+          for (int kc = 2 * pr; kc < kc_end; ++kc) {
+            const int s = (int)((T * spt + (uint32_t)kc) & 3u);
+            timed_wait(B_FULL(s), (parBf >> s) & 1u, 1);
+            timed_wait(A_FULL(s), (parAf >> s) & 1u, 2);
+            parBf ^= 1u << s; parAf ^= 1u << s;
+            tc::fence_after_sync();
+            const uint32_t bhi = sbase + s * C::STAGE_BYTES, blo = bhi + C::STAGE_BYTES / 2;
+            const uint32_t ahi = tmem + C::A_COL0 + s * 64, alo = ahi + 32;
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+              const uint32_t aa = (pass == 1) ? alo : ahi;
+              const uint32_t bb = (pass == 2) ? blo : bhi;
+#pragma unroll
+              for (int ks = 0; ks < kKC / 8; ++ks)
+                tc::mma_tf32_ts(dcol, aa + 8 * ks, tc::make_desc_ls(bb + ks * 2 * kLBO, kLBO, kSBO), idesc,
+                                ((kc - 2 * pr) | pass | ks) ? 1u : 0u);
+            }
+            tc::mma_commit(A_EMPTY(s));                            // A chunk buffer free once these MMAs complete
+            tc::mma_commit(B_EMPTY(s));                            // and so is the weight stage
+          }
+          tc::mma_commit(D_FULL(dbuf));
+        }
+      }
+      if (dbg_on && me == 0) { a.dbg[5] = dbg_t[0]; a.dbg[6] = dbg_t[1]; a.dbg[7] = dbg_t[2]; a.dbg[8] = clock64() - dbg_start;
+                               a.dbg[10] = (long long)((ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * a.kchunks; }
+    }
+  } else {
+    // ================================================================== epilogue: thread = position, 64 columns each
+    const int half = warp >= 11 ? 1 : 0;
+    const int lq = warp & 3;                                       // TMEM lane quadrant this warp may access
+    const int row = 32 * lq + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(32 * lq) << 16);
+    uint32_t pp = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      int b, lt, nt;
+      tile_pos(tile, b, lt, nt);
+      const int l = lt + row;
+      const bool pv = l < lend;
+      float acc[64];
       for (int pr = 0; pr < npairs; ++pr, ++pp) {
         const int dbuf = pp & 1;
-        timed_wait(D_FULL(dbuf), (pp >> 1) & 1, 1);
+        timed_wait(D_FULL(dbuf), (pp >> 1) & 1, 0);
         tc::fence_after_sync();
-        const long long tD0 = dbg_on ? clock64() : 0;
 #pragma unroll
-        for (int c0 = 0; c0 < NT; c0 += 32) {
+        for (int c0 = 0; c0 < 64; c0 += 32) {
           uint32_t r[32];
-          tc::tmem_ld32_nowait(lane_addr + dbuf * C::D_COLS + c0, r);
+          tc::tmem_ld32_nowait(lane_addr + dbuf * C::D_COLS + 64 * half + c0, r);
           tc::tmem_wait_ld();
           if (pr == 0) {
 #pragma unroll
@@ -367,20 +390,18 @@ __global__ void __launch_bounds__(kThreads, 1) proj_gemm_kernel(const Args a) {
         }
         tc::fence_before_sync();
         tc::mbar_arrive(D_EMPTY(dbuf));
-        if (dbg_on) dbg_t[2] += clock64() - tD0;
       }
-      const long long tS0 = dbg_on ? clock64() : 0;
-      const int nbase = nt * NT;
+      const int nbase = nt * NT + 64 * half;
       if constexpr (OUT == OUT_CH) {
         float* dst = a.out + ((size_t)b * a.N + nbase) * a.L + l;
-        if (nbase + NT <= a.N && a.bias == nullptr) {               // full tile: plain strided stores (warp = 128 bytes each)
+        if (nbase + 64 <= a.N && a.bias == nullptr) {               // full tile: plain strided stores (warp = 128 bytes each)
           if (pv) {
 #pragma unroll
-            for (int j = 0; j < NT; ++j) { *dst = acc[j]; dst += a.L; }
+            for (int j = 0; j < 64; ++j) { *dst = acc[j]; dst += a.L; }
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < NT; ++j) {
+          for (int j = 0; j < 64; ++j) {
             if (pv && nbase + j < a.N) {
               float v = acc[j];
               if (a.bias) v += __ldg(a.bias + nbase + j);
@@ -391,9 +412,9 @@ __global__ void __launch_bounds__(kThreads, 1) proj_gemm_kernel(const Args a) {
       } else {
         float* dst = a.out + ((size_t)b * a.L + l) * a.N + nbase;
         if (pv) {
-          if (nbase + NT <= a.N && (a.N & 3) == 0) {
+          if (nbase + 64 <= a.N && (a.N & 3) == 0) {
 #pragma unroll
-            for (int j = 0; j < NT / 4; ++j) {
+            for (int j = 0; j < 16; ++j) {
               float4 v = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
               if (a.bias) {
                 const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + nbase) + j);
@@ -403,79 +424,13 @@ __global__ void __launch_bounds__(kThreads, 1) proj_gemm_kernel(const Args a) {
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < NT; ++j)
+            for (int j = 0; j < 64; ++j)
               if (nbase + j < a.N) dst[j] = acc[j] + (a.bias ? __ldg(a.bias + nbase + j) : 0.f);
           }
         }
       }
-      if (dbg_on) dbg_t[3] += clock64() - tS0;
     }
-    if (dbg_on && tid == 128) { a.dbg[2] = dbg_t[1]; a.dbg[3] = dbg_t[2]; a.dbg[15] = dbg_t[3]; }
-  } else if (warp == 8) {
-    // ================================================================== bulk-copy producer (one thread)
-    if (lane == 0) {
-      const uint32_t spt = 2u * (uint32_t)((a.kchunks + 1) / 2);
-      uint32_t T = 0, parBe = 0xFu;
-      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++T) {
-        const int mt = (int)(tile / a.ntiles_n), nt = (int)(tile - (long long)mt * a.ntiles_n);
-        for (int kc = 0; kc < a.kchunks; ++kc) {
-          const int s = (int)((T * spt + (uint32_t)kc) & 3u);
-          timed_wait(B_EMPTY(s), (parBe >> s) & 1u, 2);
-          parBe ^= 1u << s;
-          tc::mbar_arrive_expect_tx(B_FULL(s), C::STAGE_BYTES);
-          const float* src = a.wimg + ((size_t)nt * a.kchunks + kc) * (C::STAGE_BYTES / 4);
-          tc::bulk_g2s(sbase + s * C::STAGE_BYTES, src, C::STAGE_BYTES, B_FULL(s));
-        }
-      }
-      if (dbg_on) { a.dbg[4] = dbg_t[2]; a.dbg[5] = clock64() - dbg_start; }
-    }
-  } else {
-    // ================================================================== MMA issuers (one thread each of warps 9 and 10)
-    // Chunk pairs alternate between the two accumulator buffers, and between the two issuing threads: a pair starts a
-    // fresh accumulation (first MMA overwrites), so the pairs are independent and no ordering is needed between the two
-    // threads' instruction streams; with chunk c on weight stage / A buffer c & 3 each issuer also owns its barriers
-    // (stages {0,1} or {2,3}), so their phases reach it in order.  While one thread sits in its barrier waits (~200 cycles each, three per chunk) the
-    // other one's MMAs keep the tensor pipe busy (measured with one issuer: 1800 cycles per chunk for 768 of MMA).
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::make_idesc(NT);
-      const uint32_t me = (uint32_t)(warp - 9);
-      uint32_t pp = 0, T = 0, parAf = 0u, parBf = 0u;
-      const int npairs = (a.kchunks + 1) / 2;
-      const uint32_t spt = 2u * (uint32_t)npairs;
-      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++T) {
-        for (int pr = 0; pr < npairs; ++pr, ++pp) {
-          if ((pp & 1u) != me) continue;
-          const int dbuf = pp & 1;
-          timed_wait(D_EMPTY(dbuf), ((pp >> 1) & 1) ^ 1, 3);       // the epilogue has drained this accumulator
-          tc::fence_after_sync();
-          const uint32_t dcol = tmem + dbuf * C::D_COLS;
-          const int kc_end = min(a.kchunks, 2 * pr + 2);
-          for (int kc = 2 * pr; kc < kc_end; ++kc) {
-            const int s = (int)((T * spt + (uint32_t)kc) & 3u), abuf = s;
-            timed_wait(B_FULL(s), (parBf >> s) & 1u, 4);
-            timed_wait(A_FULL(abuf), (parAf >> s) & 1u, 5);
-            parBf ^= 1u << s; parAf ^= 1u << s;
-            tc::fence_after_sync();
-            const uint32_t bhi = sbase + s * C::STAGE_BYTES, blo = bhi + C::STAGE_BYTES / 2;
-            const uint32_t ahi = tmem + C::A_COL0 + abuf * 64, alo = ahi + 32;
-#pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {
-              const uint32_t aa = (pass == 1) ? alo : ahi;
-              const uint32_t bb = (pass == 2) ? blo : bhi;
-#pragma unroll
-              for (int ks = 0; ks < kKC / 8; ++ks)
-                tc::mma_tf32_ts(dcol, aa + 8 * ks, tc::make_desc_ls(bb + ks * 2 * kLBO, kLBO, kSBO), idesc,
-                                ((kc - 2 * pr) | pass | ks) ? 1u : 0u);
-            }
-            tc::mma_commit(A_EMPTY(abuf));                         // A chunk buffer free once these MMAs complete
-            tc::mma_commit(B_EMPTY(s));                            // and so is the weight stage
-          }
-          tc::mma_commit(D_FULL(dbuf));
-        }
-      }
-      if (dbg_on && me == 0) { a.dbg[6] = dbg_t[3]; a.dbg[7] = dbg_t[4]; a.dbg[8] = dbg_t[5]; a.dbg[9] = clock64() - dbg_start;
-                               a.dbg[10] = nchunks; }
-    }
+    if (dbg_on && warp == 4 && lane == 0) a.dbg[9] = dbg_t[0];
   }
 
   tc::fence_before_sync();

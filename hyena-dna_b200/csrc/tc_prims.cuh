@@ -148,6 +148,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, ui
                ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(mbar)
                : "memory");
 }
+// TMA tiled copy through a tensor map (cuTensorMapEncodeTiled): box at coordinates (c0 fastest, c1) -> shared memory,
+// completion on an mbarrier (SASS: UTMALDG).  `tmap` must live in param / const / global space (__grid_constant__).
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tmap, int c0, int c1, uint32_t mbar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_dst), "l"(tmap), "r"(mbar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
 // wait (no PTX labels: may be inlined any number of times); traps after ~2 s of waiting instead of hanging the GPU --
 // a protocol bug then surfaces as a launch failure.  No suspend-time hint: with the 10 ms hint round 1 used, ptxas emits
 // SYNCS.PHASECHK + NANOSLEEP 0x989680 and the sleeping warp wakes late -- ncu put 16-32 % of all stall samples of the

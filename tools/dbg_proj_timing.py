@@ -18,10 +18,9 @@ for name, fn in cases:
     fn(); torch.cuda.synchronize(); dbg.zero_(); fn(); torch.cuda.synchronize()
     d = dbg.tolist()
     n = max(d[10], 1)
-    print(f"{name:28s} chunks/CTA {d[10]:6d}  total {d[9]/n:6.0f}/chunk | conv: wait A_EMPTY {d[0]/n:5.0f} cpwait+bar {d[11]/n:5.0f} "
-          f"stage {d[12]/n:5.0f} consume+split {d[13]/n:5.0f} st+arrive {d[14]/n:5.0f} | epi: wait D_FULL {d[2]/n:5.0f} drain {d[3]/n:5.0f} "
-          f"store {d[15]/n:5.0f} | prod: wait B_EMPTY {d[4]/n:5.0f} | MMA: wait D_EMPTY {d[6]/n:5.0f} B_FULL {d[7]/n:5.0f} "
-          f"A_FULL {d[8]/n:5.0f}  (cycles per chunk)")
+    print(f"{name:28s} chunks/CTA {d[10]:6d}  total {d[8]/n:6.0f}/chunk | conv: wait S_FULL {d[0]/n:5.0f} A_EMPTY {d[1]/n:5.0f} | producer: wait B_EMPTY "
+          f"{d[3]/n:5.0f} S_EMPTY {d[4]/n:5.0f} | MMA(0): wait D_EMPTY {d[5]/n:5.0f} B_FULL {d[6]/n:5.0f} A_FULL {d[7]/n:5.0f} | "
+          f"epi: wait D_FULL {d[9]/n:5.0f}  (cycles per chunk)")
 for name, fn in [("dWi wgrad", lambda: H.ops.proj_wgrad(ds, u)), ("dWi wgrad + FIR", lambda: H.ops.proj_wgrad(ds, u, fir=sw)),
                  ("dWo wgrad", lambda: H.ops.proj_wgrad(ych, u, transposed_out=True))]:
     fn(); torch.cuda.synchronize(); dbg.zero_(); fn(); torch.cuda.synchronize()
