@@ -14,7 +14,8 @@
 //   B operand the weights, pre-split once per call into hi / lo images in the canonical no-swizzle K-major
 //             core-matrix layout (proj_prep_kernel), streamed by TMA bulk copies (cp.async.bulk, SASS UBLKCP) into a
 //             ring of shared-memory stages guarded by mbarriers
-//   D         fp32 accumulators in TMEM, two buffers used in turn for every PAIR of K chunks (24 MMAs); the epilogue
+//   D         fp32 accumulators in TMEM, two buffers used in turn for every PAIR of K chunks (24 MMAs, the 16 small correction products
+//             first so that only the 8 hi*hi MMAs truncate at full scale); the epilogue
 //             warps drain each pair into per-thread fp32 registers (round-to-nearest adds) while the next pair is being
 //             multiplied.  Reason: the tensor core adds into its accumulator with truncation, so a long chain biases the
 //             result by ~(number of MMAs) x 2^-24 towards zero -- measured here: 96 chained MMAs (K = 256) cost 4x the
@@ -332,6 +333,12 @@ __global__ void __launch_bounds__(kThreads, 1) proj_gemm_kernel(const Args a, co
           tc::fence_after_sync();
           const uint32_t dcol = tmem + dbuf * C::D_COLS;
           const int kc_end = min(a.kchunks, 2 * pr + 2);
+          // Order inside a pair: the correction products (lo*hi, hi*lo; 2^-11 of the result) of BOTH chunks first, the
+          // hi*hi products last.  Every MMA truncates the accumulator it adds into (error ~ one-sided 2^-24 of the
+          // accumulator's magnitude), so only the 8 MMAs issued after the accumulator has reached full scale cost
+          // accuracy -- 24 did in chunk order (tools/acc_1m.py: the difference shows as a systematic shrink of y).
+          uint32_t bhi_[2], ahi_[2];
+          int ss_[2];
           for (int kc = 2 * pr; kc < kc_end; ++kc) {
             const int s = (int)((T * spt + (uint32_t)kc) & 3u);
             timed_wait(B_FULL(s), (parBf >> s) & 1u, 1);
@@ -340,17 +347,23 @@ __global__ void __launch_bounds__(kThreads, 1) proj_gemm_kernel(const Args a, co
             tc::fence_after_sync();
             const uint32_t bhi = sbase + s * C::STAGE_BYTES, blo = bhi + C::STAGE_BYTES / 2;
             const uint32_t ahi = tmem + C::A_COL0 + s * 64, alo = ahi + 32;
+            bhi_[kc - 2 * pr] = bhi; ahi_[kc - 2 * pr] = ahi; ss_[kc - 2 * pr] = s;
 #pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {
+            for (int pass = 1; pass < 3; ++pass) {
               const uint32_t aa = (pass == 1) ? alo : ahi;
               const uint32_t bb = (pass == 2) ? blo : bhi;
 #pragma unroll
               for (int ks = 0; ks < kKC / 8; ++ks)
                 tc::mma_tf32_ts(dcol, aa + 8 * ks, tc::make_desc_ls(bb + ks * 2 * kLBO, kLBO, kSBO), idesc,
-                                ((kc - 2 * pr) | pass | ks) ? 1u : 0u);
+                                ((kc - 2 * pr) | (pass - 1) | ks) ? 1u : 0u);
             }
-            tc::mma_commit(A_EMPTY(s));                            // A chunk buffer free once these MMAs complete
-            tc::mma_commit(B_EMPTY(s));                            // and so is the weight stage
+          }
+          for (int i = 0; i < kc_end - 2 * pr; ++i) {
+#pragma unroll
+            for (int ks = 0; ks < kKC / 8; ++ks)
+              tc::mma_tf32_ts(dcol, ahi_[i] + 8 * ks, tc::make_desc_ls(bhi_[i] + ks * 2 * kLBO, kLBO, kSBO), idesc, 1u);
+            tc::mma_commit(A_EMPTY(ss_[i]));                       // A chunk buffer free once these MMAs complete
+            tc::mma_commit(B_EMPTY(ss_[i]));                       // and so is the weight stage
           }
           tc::mma_commit(D_FULL(dbuf));
         }
