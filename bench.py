@@ -146,6 +146,10 @@ def kernel_algorithmic_bytes(B, D, L):
         "filter_tc_fwd": 4 * f,                          # k out
         "filter_tc_bwd": 8 * f + 7 * 64 * 4.0 * L,       # dk in, dh out, seven (64, L) arrays out
         "filter_tc_red": 4 * f + 7 * 64 * 4.0 * L,       # dh and the seven arrays in
+        # pipelined calls (HYENA_B200_PIPE: kernels of different row groups overlap, the call is timed as one record)
+        "conv_fwd<pipelined>": 8 * n + 8 * f + 8 * n + 12 * n,
+        "conv_bwd<pipelined>": 8 * n + 8 * f + 8 * n + 32 * n + 4 * f,
+        "filter_spectrum<pipelined>": 4 * f + 8 * f,
     }
 
 

@@ -23,6 +23,8 @@ static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;            // records of the current profiling window
 static std::vector<cudaEvent_t> g_ev_pool;     // recycled events
 static thread_local cudaEvent_t g_cur_e0 = nullptr;
+static thread_local bool g_prof_suppress = false;   // inside a pipelined call: the kernels of different row groups overlap, so
+                                                    // the call is timed as ONE record on the caller's stream instead
 
 static cudaEvent_t get_event() {
   if (!g_ev_pool.empty()) { cudaEvent_t e = g_ev_pool.back(); g_ev_pool.pop_back(); return e; }
@@ -32,14 +34,14 @@ static cudaEvent_t get_event() {
 }
 void prof_begin(int kind, cudaStream_t s) {
   (void)kind;
-  if (!g_prof_on) return;
+  if (!g_prof_on || g_prof_suppress) return;
   std::lock_guard<std::mutex> lk(g_prof_mu);
   g_cur_e0 = get_event();
   cudaEventRecord(g_cur_e0, s);
 }
 void prof_end(int kind, cudaStream_t s) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  if (!g_prof_on || !g_cur_e0) return;
+  if (!g_prof_on || !g_cur_e0 || g_prof_suppress) return;
   std::lock_guard<std::mutex> lk(g_prof_mu);
   cudaEvent_t e1 = get_event();
   cudaEventRecord(e1, s);
@@ -152,6 +154,72 @@ static int carve(void* ws, size_t ws_bytes, int B, int D, int L, bool backward, 
   return 0;
 }
 
+// ---------------------------------------------------------------- pipelined row groups (L2-resident scratch)
+// The three passes of a row group are enqueued back to back on one of S auxiliary streams, group g on stream g % S with
+// scratch slot g % S, G channels per group: the inter-pass scratch of a group (G x B x 8 MB at M = 2^20) is re-read while
+// it is still in the 126 MB L2, a slot is overwritten in place by the next group of its stream (dirty lines never
+// have to reach DRAM), and kernels of different groups overlap so that the short launches leave no idle tails.
+// In-stream order carries every dependency (passes of a group, reuse of a slot); the caller's stream forks into the
+// auxiliary streams and joins them again, so to the caller the call is ordered on its own stream as before.
+// HYENA_B200_PIPE="S,G" (0 = off: one launch per pass over all rows).
+struct PipeCfg { int S, G; };
+static PipeCfg pipe_cfg() {
+  static PipeCfg c = [] {
+    PipeCfg v{0, 0};
+    const char* e = getenv("HYENA_B200_PIPE");
+    int s = 0, g = 0;
+    if (e && sscanf(e, "%d,%d", &s, &g) == 2 && s >= 1 && s <= 8 && g >= 1) { v.S = s; v.G = g; }
+    return v;
+  }();
+  return c;
+}
+struct PipeDev { cudaStream_t st[8]; cudaEvent_t fork; cudaEvent_t join[8]; int n = 0; std::mutex mu; };
+static PipeDev g_pipe[64];
+static int get_pipe(int S, PipeDev** out) {
+  int dev = -1;
+  HY_CUDA(cudaGetDevice(&dev));
+  HY_CHECK(dev >= 0 && dev < 64, "unsupported device ordinal %d", dev);
+  std::lock_guard<std::mutex> lk(g_mu);
+  PipeDev& p = g_pipe[dev];
+  if (p.n == 0) HY_CUDA(cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming));
+  while (p.n < S) {
+    HY_CUDA(cudaStreamCreateWithFlags(&p.st[p.n], cudaStreamNonBlocking));
+    HY_CUDA(cudaEventCreateWithFlags(&p.join[p.n], cudaEventDisableTiming));
+    ++p.n;
+  }
+  *out = &p;
+  return 0;
+}
+// RAII: fork the caller's stream into S auxiliary streams; join() makes the caller's stream wait for all of them
+struct PipeRun {
+  PipeDev* p = nullptr; int S = 0; cudaStream_t main = nullptr; int kind = -1; bool active = false;
+  std::unique_lock<std::mutex> lk;
+  int begin(int S_, cudaStream_t main_, int kind_) {
+    S = S_; main = main_; kind = kind_;
+    if (get_pipe(S, &p)) return 1;
+    lk = std::unique_lock<std::mutex>(p->mu);
+    prof_begin(kind, main);
+    g_prof_suppress = true;
+    HY_CUDA(cudaEventRecord(p->fork, main));
+    for (int i = 0; i < S; ++i) HY_CUDA(cudaStreamWaitEvent(p->st[i], p->fork, 0));
+    active = true;
+    return 0;
+  }
+  cudaStream_t stream(int g) const { return p->st[g % S]; }
+  int join() {
+    for (int i = 0; i < S; ++i) {
+      HY_CUDA(cudaEventRecord(p->join[i], p->st[i]));
+      HY_CUDA(cudaStreamWaitEvent(main, p->join[i], 0));
+    }
+    g_prof_suppress = false;
+    active = false;
+    prof_end(kind, main);
+    g_launches.fetch_sub(1, std::memory_order_relaxed);     // the span record is not a kernel launch
+    return 0;
+  }
+  ~PipeRun() { if (active) { g_prof_suppress = false; for (int i = 0; i < S; ++i) { cudaEventRecord(p->join[i], p->st[i]); cudaStreamWaitEvent(main, p->join[i], 0); } } }
+};
+
 // Experimental (HYENA_B200_L2_PERSIST=1): mark the FFT scratch as L2-persisting for the duration of a call so that, with
 // a launch group small enough to fit (HYENA_B200_GROUP_MB <= ~64), the inter-pass intermediate stays on chip.
 struct L2Persist {
@@ -242,7 +310,8 @@ HY_API const char* hyena_b200_kind_name(int kind) {
       "col_inv<conv_fwd>", "col_inv<bwd_dg>", "col_inv<dk>", "col_inv<plain_fwd>", "col_inv<plain_bwd>",
       "row_pass<filter>", "row_pass<conv_fwd>", "row_pass<conv_bwd>",
       "filter_fwd", "filter_bwd", "short_conv_bwd", "twiddle_init", "filter_tc_prep", "filter_tc_fwd", "filter_tc_bwd", "filter_tc_red", "fused_conv_fwd",
-      "spectrum_convert", "proj_prep", "proj_gemm", "proj_wgrad"};
+      "spectrum_convert", "proj_prep", "proj_gemm", "proj_wgrad",
+      "conv_fwd<pipelined>", "conv_bwd<pipelined>", "filter_spectrum<pipelined>"};
   return (kind >= 0 && kind < K_COUNT) ? names[kind] : "?";
 }
 
@@ -258,6 +327,11 @@ HY_API size_t hyena_b200_workspace_min_bytes(int B, int D, int L, int backward) 
 
 HY_API size_t hyena_b200_workspace_bytes(int B, int D, int L, int backward) {
   if (B < 1 || L < 1 || D < 1) return 0;
+  const PipeCfg pc = pipe_cfg();
+  if (pc.S > 0) {                                   // S scratch slots of G channels each
+    const int g = pc.G < D ? pc.G : D;
+    return hyena_b200_workspace_min_bytes(B, D, L, backward) * (size_t)g * (size_t)pc.S;
+  }
   int nch = channels_per_group(group_budget_bytes(), B, D, L);
   if (nch < 1) nch = 1;
   return hyena_b200_workspace_min_bytes(B, D, L, backward) * (size_t)nch;
@@ -367,6 +441,21 @@ HY_API int hyena_b200_filter_spectrum(const float* k, float* kspec, int D, int L
   PassArgs a = base_args(1, D, L, T);
   a.A = c.A; a.src = k; a.kspec_out = reinterpret_cast<float2*>(kspec);
   a.vec = ((L & 1) == 0) && aligned8(k);
+  const PipeCfg pc = pipe_cfg();
+  const int G = pc.G < D ? pc.G : D;
+  if (pc.S > 0 && c.nch >= G * pc.S && D > G) {
+    PipeRun run;
+    if (run.begin(pc.S, s, K_PIPE_FILTER)) return 1;
+    const size_t slot = (row_bytes(L) / sizeof(float2)) * (size_t)G;
+    int g = 0;
+    for (int c0 = 0; c0 < D; c0 += G, ++g) {
+      const int n = (D - c0 < G) ? D - c0 : G;
+      a.c0 = c0; a.A = c.A + slot * (size_t)(g % pc.S);
+      HY_CUDA(launch_col_fwd(COL_FILTER, a, n, run.stream(g)));
+      HY_CUDA(launch_row_pass(ROW_FILTER, a, n, run.stream(g)));
+    }
+    return run.join();
+  }
   for (int c0 = 0; c0 < D; c0 += c.nch) {
     const int n = (D - c0 < c.nch) ? D - c0 : c.nch;
     a.c0 = c0;
@@ -439,6 +528,23 @@ HY_API int hyena_b200_core_fwd(const float* p, const float* in_bias, const float
   a.gspec = reinterpret_cast<float2*>(gspec_save);
   a.vec = ((L & 1) == 0) && aligned8(p) && aligned8(y_pre) && (!c_save || aligned8(c_save));
   a.stage = ((L & 3) == 0) && aligned16(p) && !getenv("HYENA_B200_NO_STAGE");
+  const PipeCfg pc = pipe_cfg();
+  const int G = pc.G < D ? pc.G : D;
+  if (pc.S > 0 && c.nch >= G * pc.S && D > G) {
+    PipeRun run;
+    if (run.begin(pc.S, s, K_PIPE_FWD)) return 1;
+    const size_t slot = (row_bytes(L) / sizeof(float2)) * (size_t)B * (size_t)G;
+    int g = 0;
+    for (int c0 = 0; c0 < D; c0 += G, ++g) {
+      const int n = (D - c0 < G) ? D - c0 : G;
+      cudaStream_t st = run.stream(g);
+      a.c0 = c0; a.A = c.A + slot * (size_t)(g % pc.S);
+      HY_CUDA(launch_col_fwd(COL_GATE, a, n * B, st));
+      HY_CUDA(launch_row_pass(ROW_CONV_FWD, a, n * B, st));
+      HY_CUDA(launch_col_inv(INV_CONV_FWD, a, n * B, st));
+    }
+    return run.join();
+  }
   for (int c0 = 0; c0 < D; c0 += c.nch) {
     const int n = (D - c0 < c.nch) ? D - c0 : c.nch;
     a.c0 = c0;
@@ -469,8 +575,22 @@ HY_API int hyena_b200_core_bwd(const float* dy_pre, const float* p, const float*
   a.vec = ((L & 1) == 0) && aligned8(p) && aligned8(dy_pre) && aligned8(c_saved) && aligned8(dk) &&
           aligned8(ds_scratch);
   a.stage = ((L & 3) == 0) && aligned16(p) && aligned16(dy_pre) && aligned16(c_saved) && !getenv("HYENA_B200_NO_STAGE");
-  for (int c0 = 0; c0 < D; c0 += c.nch) {
-    const int n = (D - c0 < c.nch) ? D - c0 : c.nch;
+  const PipeCfg pc = pipe_cfg();
+  const int G = pc.G < D ? pc.G : D;
+  const bool piped = pc.S > 0 && c.nch >= G * pc.S && D > G;
+  PipeRun run;
+  if (piped && run.begin(pc.S, s, K_PIPE_BWD)) return 1;
+  const int step = piped ? G : c.nch;
+  const size_t rowE = row_bytes(L) / sizeof(float2);
+  int g = 0;
+  for (int c0 = 0; c0 < D; c0 += step, ++g) {
+    const int n = (D - c0 < step) ? D - c0 : step;
+    if (piped) {                                  // slot g % S: [A: G*B rows][A2: G*B rows][A3: G rows]
+      s = run.stream(g);
+      c.A = reinterpret_cast<float2*>(workspace) + rowE * (size_t)(2 * B + 1) * (size_t)G * (size_t)(g % pc.S);
+      c.A2 = c.A + rowE * (size_t)B * (size_t)G;
+      c.A3 = c.A2 + rowE * (size_t)B * (size_t)G;
+    }
     a.c0 = c0; a.B = B;
     a.A2 = c.A2; a.A3 = c.A3;
     a.A = c.A; a.src = dy_pre;
@@ -489,6 +609,7 @@ HY_API int hyena_b200_core_bwd(const float* dy_pre, const float* p, const float*
     a.B = 1; a.out = dk;
     HY_CUDA(launch_col_inv(INV_DK, a, n, s));
   }
+  if (piped) { if (run.join()) return 1; s = (cudaStream_t)stream; }
   // pass 3 already accumulated dsw / dsb from the operand windows it had staged: no second read of p here.
   // dp == NULL: the caller consumes ds directly (hyena_b200_proj_gemm / proj_wgrad apply the transposed short filter on
   // the fly and d in_proj.bias follows from dsb and two edge samples), so dp never exists in HBM.

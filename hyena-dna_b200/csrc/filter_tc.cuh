@@ -544,7 +544,7 @@ filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const
 // K block = 32 positions (operand images: K-major, SBO 1024 B, LBO 128 B), 3xTF32 like everywhere else.
 constexpr int kRedKB = 32;
 constexpr int kRedThreads = 512;
-constexpr int kRedItems = 12;                // ceil((256 + 7*64 + 8) * 8 / 512)
+constexpr int kRedItems = 12;                // ceil(8 * roundup8(256 + 7*64 + emb_dim) / 512)
 constexpr uint32_t kRedSBO = 1024;
 __host__ __device__ constexpr uint32_t red_off(int r, int k) {
   return (uint32_t)((r >> 3) * 1024 + (k >> 2) * 128 + (r & 7) * 16 + (k & 3) * 4);
@@ -639,16 +639,20 @@ __global__ void __launch_bounds__(kRedThreads, 1) filter_tc_red_kernel(const Red
   const uint32_t tmem = *tmem_p;
 
   // Work items: (row, 4-position piece) pairs, 8 pieces per row; item w = tid + kRedThreads*it, so every item of a
-  // thread has the same piece index tid & 7.  The decode (source row pointer, destination offset, hi->lo distance
+  // thread has the same piece index (tid >> 3) & 7.  The decode (source row pointer, destination offset, hi->lo distance
   // class) does not depend on the k-block: done once, kept in registers, so that all loads of a block can be issued
   // back to back (one DRAM latency per block instead of one per item).
+  // Item -> (row, piece): inside every group of 64 items the ROW runs fastest (row = 8 (w >> 6) + (w & 7), piece =
+  // (w >> 3) & 7), so the eight lanes of a quarter warp write the eight 16-byte rows of ONE core matrix = 128 contiguous
+  // bytes (conflict free), and a warp reads 64 contiguous bytes of each of eight rows.  (Piece-fastest, as in round 1,
+  // put the eight lanes 128 bytes apart: an 8-way bank conflict on every store, 87 % of all shared wavefronts.)
   const int nrow = R.D + 7 * 64 + R.E;                     // dh rows, six (64,L) arrays + X, z rows
-  const int pc = tid & 7;
+  const int pc = (tid >> 3) & 7;
   const float* sp[kRedItems];
   uint32_t dof[kRedItems];                                 // bits [0,18): byte offset of the hi piece; [18,20): lo class
   static_for<0, kRedItems>([&](auto it_) {
     constexpr int it = decltype(it_)::value;
-    const int row = (tid + kRedThreads * it) >> 3;
+    const int row = (((tid + kRedThreads * it) >> 6) << 3) + (tid & 7);
     const float* src = nullptr;
     uint32_t img = 0, cls = 0;
     int r = 0;

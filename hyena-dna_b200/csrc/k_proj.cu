@@ -1,4 +1,5 @@
 // Launchers of the tcgen05 projection GEMMs (proj_gemm.cuh).
+#include <cstdint>
 #include <cstring>
 
 #include "launch.h"
@@ -41,6 +42,20 @@ static bool make_tmap(CUtensorMap* m, const float* base, unsigned long long rows
   return f(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// fp32 tensor (d2, d1, d0) with d0 contiguous -> 3-D tensor map with box (b0 x b1 x 1)
+static bool make_tmap3(CUtensorMap* m, const float* base, unsigned long long d0, unsigned long long d1, unsigned long long d2,
+                       unsigned b0, unsigned b1) {
+  EncodeTiledFn f = encode_tiled();
+  if (!f) return false;
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {d0 * sizeof(float), d0 * d1 * sizeof(float)};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return f(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <int NT, int ACT, int OUT>
@@ -132,11 +147,19 @@ cudaError_t launch_proj_wgrad(const float* X, const float* Y, const float* fir, 
   proj_wgrad_plan(M, N, sms, &a.mtiles, &a.ntiles, &a.splits);
   const long long total_chunks = (long long)B * a.chunks_per_b;
   if (a.splits > total_chunks) a.splits = (int)total_chunks;
-  a.vec = (L % 4 == 0) && (N % 4 == 0);
+  a.vec = (L % 4 == 0) && (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y)) & 15u) == 0;
+  CUtensorMap tmx, tmy;
+  memset(&tmx, 0, sizeof(tmx)); memset(&tmy, 0, sizeof(tmy));
+  if (a.vec) {
+    // X (B, M, L): box 36 positions x 128 rows;  Y (B, L, N): box 128 columns x 32 positions
+    const bool ok = make_tmap3(&tmx, X, (unsigned long long)L, (unsigned long long)M, (unsigned long long)B, 36, 128) &&
+                    make_tmap3(&tmy, Y, (unsigned long long)N, (unsigned long long)L, (unsigned long long)B, 128, 32);
+    if (!ok) a.vec = 0;                  // no driver entry point / unencodable shape: the producer warp stages by hand
+  }
   cudaError_t e = cudaFuncSetAttribute(wg::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg::kSmem);
   if (e != cudaSuccess) return e;
   prof_begin(K_PROJ_WGRAD, s);
-  wg::wgrad_kernel<<<a.mtiles * a.ntiles * a.splits, wg::kThreads, wg::kSmem, s>>>(a);
+  wg::wgrad_kernel<<<a.mtiles * a.ntiles * a.splits, wg::kThreads, wg::kSmem, s>>>(a, tmx, tmy);
   prof_end(K_PROJ_WGRAD, s);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;

@@ -38,7 +38,7 @@ namespace hy {
 namespace pg {
 
 constexpr int kKC = 32;                 // K chunk (one chunk = 4 MMAs of K = 8 per product)
-constexpr int kThreads = 480;          // 15 warps: 4 convert, 8 epilogue, 1 TMA producer, 2 MMA issuers
+constexpr int kThreads = 512;          // 16 warps: 4 convert, 8 epilogue, 2 TMA producers (weights / activations), 2 MMA issuers
 constexpr uint32_t kSBO = 1024, kLBO = 128;
 constexpr uint32_t kAPitchCh = 132 * 4; // ACT_CH staging row: 128 positions + one look-ahead quad (fused FIR)
 constexpr uint32_t kAStageBytes = 32 * kAPitchCh;      // 16.5 KB (>= the 16 KB an ACT_ROW tile needs)
@@ -120,11 +120,13 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// Warp roles (480 threads):
+// Warp roles (512 threads):
 //   warps 0-3    convert: staged activation chunk -> registers (-> fused FIR) -> (hi, lo) split -> tensor memory
 //   warps 4-7    epilogue, output columns [0, 64)   } thread = position; drain every chunk pair into registers,
 //   warps 11-14  epilogue, output columns [64, 128) } store the tile at the end
-//   warp 8       producer: TMA bulk copies of the weight images (lane 0) and of the activation rows (all lanes)
+//   warp 8       producer: TMA bulk copies of the weight images (lane 0); stages the activation by hand when it does
+//                not qualify for TMA (all lanes)
+//   warp 15      producer: tiled TMA copies of the activation tiles (lane 0)
 //   warps 9, 10  MMA issuers (lane 0 each), alternate chunk pairs
 template <int NT, int ACT, int OUT>
 __global__ void __launch_bounds__(kThreads, 1) proj_gemm_kernel(const Args a, const __grid_constant__ CUtensorMap tmap) {
@@ -259,31 +261,41 @@ __global__ void __launch_bounds__(kThreads, 1) proj_gemm_kernel(const Args a, co
     // aligned) are staged by the 32 lanes with plain loads and stores instead.
     if (lane == 0 && a.vec) tc::tma_prefetch_desc(&tmap);
     uint32_t T = 0, parBe = 0xFu, parSe = 0xFu;
+    if (a.vec) {
+      // Two independent issue loops (this lane: weights; warp 15: activation tiles): the activation copy of a chunk only needs its staging slot back (the
+      // converters release it as soon as they have read it), the weight copy needs the MMAs of four chunks ago to have
+      // completed.  Issued from one loop the activation stream ran a whole weight-stage wait late (measured: converters
+      // waiting ~970 of 1650 cycles per chunk for their tile).
+      if (lane == 0) {
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++T) {
+          int b, lt, nt;
+          tile_pos(tile, b, lt, nt);
+          for (int kc = 0; kc < a.kchunks; ++kc) {
+            const int s = (int)((T * spt + (uint32_t)kc) & 3u);
+            timed_wait(B_EMPTY(s), (parBe >> s) & 1u, 0);
+            parBe ^= 1u << s;
+            tc::mbar_arrive_expect_tx(B_FULL(s), C::STAGE_BYTES);
+            const float* src = a.wimg + ((size_t)nt * a.kchunks + kc) * (C::STAGE_BYTES / 4);
+            tc::bulk_g2s(sbase + s * C::STAGE_BYTES, src, C::STAGE_BYTES, B_FULL(s));
+          }
+        }
+      }
+    } else
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++T) {
       int b, lt, nt;
       tile_pos(tile, b, lt, nt);
       for (int kc = 0; kc < a.kchunks; ++kc) {
         const int s = (int)((T * spt + (uint32_t)kc) & 3u);
         const int k0 = kc * kKC;
-        const uint32_t st_u = sbase + (uint32_t)C::OFF_A + (uint32_t)s * kSStageBytes;
         if (lane == 0) {
           timed_wait(B_EMPTY(s), (parBe >> s) & 1u, 0);
           tc::mbar_arrive_expect_tx(B_FULL(s), C::STAGE_BYTES);
           const float* src = a.wimg + ((size_t)nt * a.kchunks + kc) * (C::STAGE_BYTES / 4);
           tc::bulk_g2s(sbase + s * C::STAGE_BYTES, src, C::STAGE_BYTES, B_FULL(s));
           timed_wait(S_EMPTY(s), (parSe >> s) & 1u, 1);
-          if (a.vec) {
-            if constexpr (ACT == ACT_ROW) {
-              tc::mbar_arrive_expect_tx(S_FULL(s), 128u * 128u);
-              tc::tma_load_2d(st_u, &tmap, k0, b * a.L + lt, S_FULL(s));
-            } else {
-              tc::mbar_arrive_expect_tx(S_FULL(s), 32u * kAPitchCh);
-              tc::tma_load_2d(st_u, &tmap, lt, b * a.K + k0, S_FULL(s));
-            }
-          }
         }
         parBe ^= 1u << s; parSe ^= 1u << s;
-        if (!a.vec) {
+        {
           __syncwarp();
           unsigned char* st = smem + C::OFF_A + (size_t)s * kSStageBytes;
           if constexpr (ACT == ACT_ROW) {
@@ -313,7 +325,31 @@ __global__ void __launch_bounds__(kThreads, 1) proj_gemm_kernel(const Args a, co
         }
       }
     }
-    if (dbg_on && lane == 0) { a.dbg[3] = dbg_t[0]; a.dbg[4] = dbg_t[1]; }
+    if (dbg_on && lane == 0) { a.dbg[3] = dbg_t[0]; if (!a.vec) a.dbg[4] = dbg_t[1]; }
+  } else if (warp == 15) {
+    // ================================================================== producer: activation tiles (TMA), own warp
+    if (lane == 0 && a.vec) {
+      uint32_t T = 0, parSe = 0xFu;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++T) {
+        int b, lt, nt;
+        tile_pos(tile, b, lt, nt);
+        for (int kc = 0; kc < a.kchunks; ++kc) {
+          const int s = (int)((T * spt + (uint32_t)kc) & 3u);
+          const int k0 = kc * kKC;
+          const uint32_t st_u = sbase + (uint32_t)C::OFF_A + (uint32_t)s * kSStageBytes;
+          timed_wait(S_EMPTY(s), (parSe >> s) & 1u, 1);
+          parSe ^= 1u << s;
+          if constexpr (ACT == ACT_ROW) {
+            tc::mbar_arrive_expect_tx(S_FULL(s), 128u * 128u);
+            tc::tma_load_2d(st_u, &tmap, k0, b * a.L + lt, S_FULL(s));
+          } else {
+            tc::mbar_arrive_expect_tx(S_FULL(s), 32u * kAPitchCh);
+            tc::tma_load_2d(st_u, &tmap, lt, b * a.K + k0, S_FULL(s));
+          }
+        }
+      }
+      if (dbg_on) a.dbg[4] = dbg_t[1];
+    }
   } else if (warp == 9 || warp == 10) {
     // ================================================================== MMA issuers (one thread each of warps 9 and 10)
     // Chunk pairs alternate between the two accumulator buffers, and between the two issuing threads: a pair starts a
@@ -371,7 +407,7 @@ __global__ void __launch_bounds__(kThreads, 1) proj_gemm_kernel(const Args a, co
       if (dbg_on && me == 0) { a.dbg[5] = dbg_t[0]; a.dbg[6] = dbg_t[1]; a.dbg[7] = dbg_t[2]; a.dbg[8] = clock64() - dbg_start;
                                a.dbg[10] = (long long)((ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * a.kchunks; }
     }
-  } else {
+  } else if (warp != 15) {
     // ================================================================== epilogue: thread = position, 64 columns each
     const int half = warp >= 11 ? 1 : 0;
     const int lq = warp & 3;                                       // TMEM lane quadrant this warp may access
@@ -475,10 +511,10 @@ __global__ void __launch_bounds__(kThreads, 1) proj_gemm_kernel(const Args a, co
 //             separate CORRECTION accumulator, 2^-11 times smaller, whose own bias is negligible over the whole slice.
 namespace wg {
 
-constexpr int kThreads = 416;             // warps 0-3 Y staging + A conversion, 4-7 X staging + B images, 8 MMA, 9-12 drain
+constexpr int kThreads = 448;             // warps 0-3 Y -> A conversion, 4-7 X -> B images, 8 MMA, 9-12 drain, 13 TMA producer
 constexpr int kSeg = 8;                   // chunks per accumulation segment (32 chained main MMAs)
-constexpr int kStg = 3;                   // staged chunks in flight
-constexpr uint32_t kYPitch = 132 * 4;     // staged Y row: 128 columns (+pad)
+constexpr int kStg = 4;                   // staged chunks in flight
+constexpr uint32_t kYPitch = 128 * 4;     // staged Y row: 128 columns, dense (= the TMA box)
 constexpr uint32_t kYStage = 32 * kYPitch;            // 32 positions
 constexpr uint32_t kXPitch = 36 * 4;      // staged X row: 32 positions + one look-ahead quad (fused FIR)
 constexpr uint32_t kXStage = 128 * kXPitch;           // 128 rows
@@ -488,6 +524,8 @@ constexpr uint32_t kOffImg = (kOffX + kStg * kXStage + 1023u) & ~1023u;         
 constexpr uint32_t kOffBar = kOffImg + 2 * 2 * kImg;
 constexpr size_t kSmem = kOffBar + 256;
 static_assert(kOffImg % 1024 == 0, "operand images must start on a core-matrix group boundary");
+static_assert(kYStage % 128 == 0 && kXStage % 128 == 0, "TMA destinations are 128-byte aligned");
+static_assert(kSmem <= 227 * 1024, "shared memory budget");
 
 struct Args {
   const float* X;       // (B, M, L)
@@ -498,14 +536,22 @@ struct Args {
   int B, L, M, N;
   int chunks_per_b;     // ceil(L / 32)
   int mtiles, ntiles, splits;
-  int vec;              // 16-byte cp.async staging legal
+  int vec;              // 1: both tensors qualify for TMA (16-byte aligned rows): the tensor maps are valid
 };
 
-__global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a) {
+// Staging: one producer thread issues, per chunk of 32 positions, ONE tiled TMA copy of the Y tile (box 128 n x 32 pos of
+// the (N, L, B) tensor) and one of the X tile (box 36 pos x 128 m of the (L, M, B) tensor; four look-ahead samples for
+// the fused FIR), four chunks in flight, completion on an mbarrier per stage.  Out-of-range rows / columns / positions
+// are zero-filled by the copy engine (tails of M, N and L; the 3-D maps keep a tile from running into the next batch).
+// Round 2 measured why: staged with per-thread cp.async the kernel sat at ~3100 cycles per chunk for 800 of MMA, both
+// staging loops waiting ~900 cycles just to ISSUE their copies (the SM's outstanding-miss tracking was full);
+// bulk tensor copies do not go through it.
+__global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a, const __grid_constant__ CUtensorMap tmapX,
+                                                            const __grid_constant__ CUtensorMap tmapY) {
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
-  // barriers: b_full[2] b_empty[2] a_full[2] a_empty[2] dm_full[2] dm_empty[2] dc_full
-  uint32_t* tmem_p = reinterpret_cast<uint32_t*>(bars + 13);
+  // barriers: b_full[2] b_empty[2] a_full[2] a_empty[2] dm_full[2] dm_empty[2] dc_full s_full[4] y_empty[4] x_empty[4]
+  uint32_t* tmem_p = reinterpret_cast<uint32_t*>(bars + 25);
   const uint32_t sbase = tc::smem_u32(smem), bar0 = tc::smem_u32(bars);
   auto B_FULL = [&](int s) { return bar0 + 8u * s; };
   auto B_EMPTY = [&](int s) { return bar0 + 8u * (2 + s); };
@@ -514,6 +560,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a) {
   auto DM_FULL = [&](int j) { return bar0 + 8u * (8 + j); };
   auto DM_EMPTY = [&](int j) { return bar0 + 8u * (10 + j); };
   const uint32_t DC_FULL = bar0 + 8u * 12;
+  auto S_FULL = [&](int j) { return bar0 + 8u * (13 + j); };
+  auto Y_EMPTY = [&](int j) { return bar0 + 8u * (17 + j); };
+  auto X_EMPTY = [&](int j) { return bar0 + 8u * (21 + j); };
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // tensor memory map (columns): main accumulators [0,128) [128,256), correction accumulator [256,384), A chunks [384,512)
   constexpr uint32_t kColDC = 256, kColA = 384;
@@ -530,6 +579,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a) {
       tc::mbar_init(DM_FULL(s), 1); tc::mbar_init(DM_EMPTY(s), 128);
     }
     tc::mbar_init(DC_FULL, 1);
+    for (int j = 0; j < kStg; ++j) { tc::mbar_init(S_FULL(j), 1); tc::mbar_init(Y_EMPTY(j), 128); tc::mbar_init(X_EMPTY(j), 128); }
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -558,52 +608,15 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a) {
   if (warp < 4) {
     // ---------------------------------------------------------------- A side: thread = column n of Y = TMEM lane
     const uint32_t lane_addr = tmem + ((uint32_t)(32 * warp) << 16);
-    // chunk cursor (batch, first position), advanced incrementally: no 64-bit divisions in the loop
-    int sb_ = (int)(c_begin / a.chunks_per_b), sl_ = (int)(c_begin - (long long)sb_ * a.chunks_per_b) * 32;
-    auto stage = [&](long long q) {                                     // Y[l0 .. l0+32)[n0 .. n0+128) -> slot q % kStg
-      const int b = sb_, l0 = sl_;
-      sl_ += 32;
-      if (sl_ >= a.chunks_per_b * 32) { sl_ = 0; ++sb_; }
-      unsigned char* st = smem + kOffY + (size_t)(q % kStg) * kYStage;
-      const int k0_ = tid >> 5, q32 = tid & 31;                          // pieces (position k0_ + 4 i, quad q32), i < 8
-      if (a.vec && l0 + 32 <= a.L && n0 + 128 <= a.N) {                  // interior chunk: no predicates
-        const float* src = a.Y + ((size_t)b * a.L + l0 + k0_) * a.N + n0 + 4 * q32;
-        unsigned char* dst = st + k0_ * kYPitch + q32 * 16;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) cp_async16(dst + i * 4 * kYPitch, src + (size_t)i * 4 * a.N, true);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int k = k0_ + 4 * i, qd = q32;
-          const int l = l0 + k, n = n0 + 4 * qd;
-          const float* src = a.Y + ((size_t)b * a.L + (l < a.L ? l : 0)) * a.N;
-          unsigned char* dst = st + k * kYPitch + qd * 16;
-          if (a.vec) {
-            const bool ok = (l < a.L) && (n + 4 <= a.N);
-            cp_async16(dst, src + (ok ? n : 0), ok);
-          } else {
-            float4 v;
-            v.x = (l < a.L && n + 0 < a.N) ? __ldg(src + n + 0) : 0.f;
-            v.y = (l < a.L && n + 1 < a.N) ? __ldg(src + n + 1) : 0.f;
-            v.z = (l < a.L && n + 2 < a.N) ? __ldg(src + n + 2) : 0.f;
-            v.w = (l < a.L && n + 3 < a.N) ? __ldg(src + n + 3) : 0.f;
-            *reinterpret_cast<float4*>(dst) = v;
-          }
-        }
-      }
-      cp_async_commit();
-    };
-    for (int q = 0; q < kStg - 1; ++q) {
-      if (q < nchunks) stage(q); else cp_async_commit();
-    }
     for (long long q = 0; q < nchunks; ++q) {
-      cp_async_wait_group<kStg - 2>();
-      pg::named_bar_sync(1, 128);
-      const long long tS = dbg_on ? clock64() : 0;
-      if (q + kStg - 1 < nchunks) stage(q + kStg - 1); else cp_async_commit();
+      const int ss = (int)(q % kStg);
+      {
+        const long long tS = dbg_on ? clock64() : 0;
+        tc::mbar_wait_u(S_FULL(ss), (uint32_t)(q / kStg) & 1u);         // the producer's copies of this chunk have landed
+        if (dbg_on) dbg_t[1] += clock64() - tS;
+      }
       const long long tC = dbg_on ? clock64() : 0;
-      if (dbg_on) dbg_t[1] += tC - tS;
-      const unsigned char* st = smem + kOffY + (size_t)(q % kStg) * kYStage;
+      const unsigned char* st = smem + kOffY + (size_t)ss * kYStage;
       uint32_t hi[32], lo[32];
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
@@ -612,6 +625,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a) {
         tc::split_tf32(v, h, lw);
         hi[k] = __float_as_uint(h); lo[k] = __float_as_uint(lw);
       }
+      tc::mbar_arrive(Y_EMPTY(ss));                                     // staged tile consumed: the producer may refill the slot
       const uint32_t it = (uint32_t)q;
       const int buf = it & 1;
       if (dbg_on) dbg_t[2] += clock64() - tC;
@@ -624,51 +638,12 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a) {
       tc::fence_before_sync();
       tc::mbar_arrive(A_FULL(buf));
     }
-    cp_async_wait_all();
     if (dbg_on && tid == 0) { a.dbg[0] = dbg_t[0]; a.dbg[1] = dbg_t[1]; a.dbg[2] = dbg_t[2]; a.dbg[15] = nchunks;
                               a.dbg[14] = clock64() - dbg_start; }
   } else if (warp < 8) {
     // ---------------------------------------------------------------- B side: X rows -> K-major hi / lo images
     const int t = tid - 128;
     const bool use_fir = a.fir != nullptr;
-    int sb_ = (int)(c_begin / a.chunks_per_b), sl_ = (int)(c_begin - (long long)sb_ * a.chunks_per_b) * 32;
-    auto stage = [&](long long q) {                                     // X[m0 .. m0+128)[l0 .. l0+32(+4)) -> slot q % kStg
-      const int b = sb_, l0 = sl_;
-      sl_ += 32;
-      if (sl_ >= a.chunks_per_b * 32) { sl_ = 0; ++sb_; }
-      unsigned char* st = smem + kOffX + (size_t)(q % kStg) * kXStage;
-      auto piece = [&](int r, int qd) {
-        const int m = m0 + r, l = l0 + 4 * qd;
-        const float* src = a.X + ((size_t)b * a.M + (m < a.M ? m : 0)) * a.L;
-        unsigned char* dst = st + r * kXPitch + qd * 16;
-        if (a.vec) {
-          const bool ok = (m < a.M) && (l + 4 <= a.L);
-          cp_async16(dst, src + (ok ? l : 0), ok);
-        } else {
-          float4 v;
-          v.x = (m < a.M && l + 0 < a.L) ? __ldg(src + l + 0) : 0.f;
-          v.y = (m < a.M && l + 1 < a.L) ? __ldg(src + l + 1) : 0.f;
-          v.z = (m < a.M && l + 2 < a.L) ? __ldg(src + l + 2) : 0.f;
-          v.w = (m < a.M && l + 3 < a.L) ? __ldg(src + l + 3) : 0.f;
-          *reinterpret_cast<float4*>(dst) = v;
-        }
-      };
-      // 128 rows x 8 quads (row (t >> 3) + 16 i, quad t & 7), eight pieces per thread, plus the look-ahead quad of row t
-      // (fused FIR)
-      if (a.vec && m0 + 128 <= a.M && l0 + 32 + (use_fir ? 4 : 0) <= a.L) {   // interior chunk: no predicates
-        const float* base = a.X + ((size_t)b * a.M + m0) * a.L + l0;
-        const float* src = base + (size_t)(t >> 3) * a.L + 4 * (t & 7);
-        unsigned char* dst = st + (t >> 3) * kXPitch + (t & 7) * 16;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) cp_async16(dst + i * 16 * kXPitch, src + (size_t)i * 16 * a.L, true);
-        if (use_fir) cp_async16(st + t * kXPitch + 128, base + (size_t)t * a.L + 32, true);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) piece((t >> 3) + 16 * i, t & 7);
-        if (use_fir) piece(t, 8);
-      }
-      cp_async_commit();
-    };
     // this thread converts pieces (row r, quad k4) with r % 8 == t % 8: the eight lanes of a quarter warp then write one
     // contiguous 128-byte core matrix (bank-conflict free); 1024 pieces per chunk, 8 per thread
     const int rlo = t & 7, kq = (t >> 3) & 7, rhi0 = t >> 6;            // rows r = rlo + 8 * (rhi0 + 2 i), i < 8
@@ -681,16 +656,14 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a) {
         for (int j = 0; j < 3; ++j) w[i][j] = (m < a.M) ? __ldg(a.fir + 3 * m + j) : 0.f;
       }
     }
-    for (int q = 0; q < kStg - 1; ++q) {
-      if (q < nchunks) stage(q); else cp_async_commit();
-    }
     for (long long q = 0; q < nchunks; ++q) {
-      cp_async_wait_group<kStg - 2>();
-      pg::named_bar_sync(2, 128);
-      const long long tS = dbg_on ? clock64() : 0;
-      if (q + kStg - 1 < nchunks) stage(q + kStg - 1); else cp_async_commit();
-      if (dbg_on) dbg_t[1] += clock64() - tS;
-      const unsigned char* st = smem + kOffX + (size_t)(q % kStg) * kXStage;
+      const int ss = (int)(q % kStg);
+      {
+        const long long tS = dbg_on ? clock64() : 0;
+        tc::mbar_wait_u(S_FULL(ss), (uint32_t)(q / kStg) & 1u);
+        if (dbg_on) dbg_t[1] += clock64() - tS;
+      }
+      const unsigned char* st = smem + kOffX + (size_t)ss * kXStage;
       const uint32_t it = (uint32_t)q;
       const int s = it & 1;
       timed_wait(B_EMPTY(s), ((it >> 1) & 1) ^ 1, 0);                   // the MMAs that read this image pair are done
@@ -719,11 +692,11 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a) {
         *reinterpret_cast<float4*>(hi_img + off) = h;
         *reinterpret_cast<float4*>(lo_img + off) = lw;
       }
+      tc::mbar_arrive(X_EMPTY(ss));                                     // staged rows consumed
       tc::fence_async_smem();
       tc::mbar_arrive(B_FULL(s));
       if (dbg_on) dbg_t[2] += clock64() - tV;
     }
-    cp_async_wait_all();
     if (dbg_on && t == 0) { a.dbg[3] = dbg_t[0]; a.dbg[4] = dbg_t[1]; a.dbg[5] = dbg_t[2]; }
   } else {
     // ---------------------------------------------------------------- MMA issuer
@@ -761,7 +734,41 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a) {
       if (dbg_on) { a.dbg[6] = dbg_t[0]; a.dbg[7] = dbg_t[1]; a.dbg[8] = dbg_t[2]; a.dbg[9] = clock64() - dbg_start; }
     }
   }
-  if (warp >= 9) {
+  if (warp == 13) {
+    // ---------------------------------------------------------------- producer: Y and X tiles of every chunk (TMA)
+    if (lane == 0 && a.vec) { tc::tma_prefetch_desc(&tmapX); tc::tma_prefetch_desc(&tmapY); }
+    int sb_ = (int)(c_begin / a.chunks_per_b), sl_ = (int)(c_begin - (long long)sb_ * a.chunks_per_b) * 32;
+    for (long long q = 0; q < nchunks; ++q) {
+      const int ss = (int)(q % kStg);
+      const uint32_t par = ((uint32_t)(q / kStg) & 1u) ^ 1u;
+      const int b = sb_, l0 = sl_;
+      sl_ += 32;
+      if (sl_ >= a.chunks_per_b * 32) { sl_ = 0; ++sb_; }
+      tc::mbar_wait_u(Y_EMPTY(ss), par);
+      tc::mbar_wait_u(X_EMPTY(ss), par);
+      if (a.vec) {
+        if (lane == 0) {
+          tc::mbar_arrive_expect_tx(S_FULL(ss), kYStage + kXStage);
+          tc::tma_load_3d(sbase + kOffY + ss * kYStage, &tmapY, n0, l0, b, S_FULL(ss));
+          tc::tma_load_3d(sbase + kOffX + ss * kXStage, &tmapX, l0, m0, b, S_FULL(ss));
+        }
+      } else {
+        // rows that do not qualify for TMA: the 32 lanes stage the tiles with plain loads (zero fill outside the tensors)
+        float* ys = reinterpret_cast<float*>(smem + kOffY + (size_t)ss * kYStage);
+        for (int i = lane; i < 32 * 128; i += 32) {
+          const int k = i >> 7, n = i & 127, l = l0 + k;
+          ys[i] = (l < a.L && n0 + n < a.N) ? __ldg(a.Y + ((size_t)b * a.L + l) * a.N + n0 + n) : 0.f;
+        }
+        float* xs = reinterpret_cast<float*>(smem + kOffX + (size_t)ss * kXStage);
+        for (int i = lane; i < 128 * 36; i += 32) {
+          const int r = i / 36, e = i - r * 36, l = l0 + e;
+          xs[i] = (m0 + r < a.M && l < a.L) ? __ldg(a.X + ((size_t)b * a.M + m0 + r) * a.L + l) : 0.f;
+        }
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(S_FULL(ss));
+      }
+    }
+  } else if (warp >= 9) {
     // ---------------------------------------------------------------- drain warps: thread = accumulator row (TMEM lane)
     const int w4 = warp - 9, row = 32 * w4 + lane;                      // warps 9..12 -> lane quadrants 1,2,3,0
     const int lq = warp & 3;

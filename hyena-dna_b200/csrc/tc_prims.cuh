@@ -155,6 +155,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tmap,
                ::"r"(smem_dst), "l"(tmap), "r"(mbar), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const void* tmap, int c0, int c1, int c2, uint32_t mbar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_dst), "l"(tmap), "r"(mbar), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }

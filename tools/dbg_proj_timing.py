@@ -25,7 +25,7 @@ for name, fn in [("dWi wgrad", lambda: H.ops.proj_wgrad(ds, u)), ("dWi wgrad + F
                  ("dWo wgrad", lambda: H.ops.proj_wgrad(ych, u, transposed_out=True))]:
     fn(); torch.cuda.synchronize(); dbg.zero_(); fn(); torch.cuda.synchronize()
     d = dbg.tolist(); n = max(d[15], 1)
-    print(f"{name:18s} chunks/CTA {d[15]:5d} total {d[9]/n:6.0f}/chunk | A side: wait A_EMPTY {d[0]/n:5.0f} stage {d[1]/n:5.0f} consume {d[2]/n:5.0f} "
-          f"| B side: wait B_EMPTY {d[3]/n:5.0f} stage {d[4]/n:5.0f} convert {d[5]/n:5.0f} | MMA: wait DM_EMPTY {d[6]/n:5.0f} B_FULL {d[7]/n:5.0f} "
+    print(f"{name:18s} chunks/CTA {d[15]:5d} total {d[9]/n:6.0f}/chunk | A side: wait A_EMPTY {d[0]/n:5.0f} S_FULL {d[1]/n:5.0f} consume {d[2]/n:5.0f} "
+          f"| B side: wait B_EMPTY {d[3]/n:5.0f} S_FULL {d[4]/n:5.0f} convert {d[5]/n:5.0f} | MMA: wait DM_EMPTY {d[6]/n:5.0f} B_FULL {d[7]/n:5.0f} "
           f"A_FULL {d[8]/n:5.0f} | drain: wait DM_FULL {d[10]/n:5.0f} drain {d[11]/n:5.0f}  (cycles per chunk)")
 H._lib.lib().hyena_b200_proj_debug_buffer(0)
