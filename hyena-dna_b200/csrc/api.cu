@@ -311,7 +311,7 @@ HY_API const char* hyena_b200_kind_name(int kind) {
       "row_pass<filter>", "row_pass<conv_fwd>", "row_pass<conv_bwd>",
       "filter_fwd", "filter_bwd", "short_conv_bwd", "twiddle_init", "filter_tc_prep", "filter_tc_fwd", "filter_tc_bwd", "filter_tc_red", "fused_conv_fwd",
       "spectrum_convert", "proj_prep", "proj_gemm", "proj_wgrad",
-      "conv_fwd<pipelined>", "conv_bwd<pipelined>", "filter_spectrum<pipelined>"};
+      "conv_fwd<pipelined>", "conv_bwd<pipelined>", "filter_spectrum<pipelined>", "add_layer_norm"};
   return (kind >= 0 && kind < K_COUNT) ? names[kind] : "?";
 }
 
@@ -709,6 +709,32 @@ HY_API int hyena_b200_fftconv_bwd(const float* dout, const float* u, const float
     a.B = 1; a.out = dk;
     HY_CUDA(launch_col_inv(INV_DK, a, n, s));
   }
+  return 0;
+}
+
+/* y = LayerNorm(x + res) * w + b, res_out = x + res (flash_attn/modules/block.py:111-148, pre-norm Block) */
+HY_API size_t hyena_b200_add_layernorm_scratch_bytes(long long rows, int D) {
+  return (rows < 1 || D < 1) ? 0 : (size_t)ln_partials(rows) * 2 * (size_t)D * sizeof(float);
+}
+
+HY_API int hyena_b200_add_layernorm_fwd(const float* x, const float* res, const float* w, const float* b, float eps,
+                                 float* res_out, float* y, float* mean, float* rstd, long long rows, int D, void* stream) {
+  HY_CHECK(rows >= 1 && D >= 1, "bad shape rows=%lld D=%d", rows, D);
+  HY_CHECK(x && w && y && mean && rstd, "null pointer");
+  HY_CHECK(res == nullptr || res_out != nullptr, "res_out is required when a residual is added");
+  ln::FwdArgs a{x, res, w, b, res_out, y, mean, rstd, rows, D, eps};
+  HY_CUDA(launch_add_ln_fwd(a, (cudaStream_t)stream));
+  return 0;
+}
+
+HY_API int hyena_b200_add_layernorm_bwd(const float* dy, const float* dres, const float* r, const float* w, const float* mean,
+                                 const float* rstd, float* dx, float* dw, float* db, long long rows, int D, void* scratch,
+                                 size_t scratch_bytes, void* stream) {
+  HY_CHECK(rows >= 1 && D >= 1, "bad shape rows=%lld D=%d", rows, D);
+  HY_CHECK(dy && r && w && mean && rstd && dx && dw && scratch, "null pointer");
+  HY_CHECK(scratch_bytes >= hyena_b200_add_layernorm_scratch_bytes(rows, D), "scratch too small (%zu bytes)", scratch_bytes);
+  ln::BwdArgs a{dy, dres, r, w, mean, rstd, dx, reinterpret_cast<float*>(scratch), rows, D};
+  HY_CUDA(launch_add_ln_bwd(a, dw, db, (cudaStream_t)stream));
   return 0;
 }
 

@@ -3,6 +3,7 @@
 #include "fft_passes.cuh"
 #include "filter_mlp.cuh"
 #include "short_conv.cuh"
+#include "layernorm_args.h"
 
 namespace hy {
 
@@ -14,7 +15,8 @@ enum Kind {
   K_FILTER_FWD = 12, K_FILTER_BWD = 13, K_SHORT_BWD = 14, K_TWIDDLE = 15, K_FILTER_TC_PREP = 16, K_FILTER_TC_FWD = 17,
   K_FILTER_TC_BWD = 18, K_FILTER_TC_RED = 19, K_FUSED_FWD = 20, K_CONVERT = 21, K_PROJ_PREP = 22, K_PROJ_GEMM = 23, K_PROJ_WGRAD = 24,
   K_PIPE_FWD = 25, K_PIPE_BWD = 26, K_PIPE_FILTER = 27,   // whole pipelined calls (api.cu PipeRun): kernels of different groups overlap
-  K_COUNT = 28
+  K_ADD_LN = 28,            // residual add + LayerNorm (block glue, layernorm.cuh)
+  K_COUNT = 29
 };
 void prof_begin(int kind, cudaStream_t s);     // api.cu: records an event when profiling is on
 void prof_end(int kind, cudaStream_t s);       // api.cu: records an event when profiling is on; counts the launch
@@ -41,6 +43,10 @@ cudaError_t launch_proj_gemm(const float* act, int act_layout, const float* W, i
 size_t proj_wgrad_scratch_bytes(int M, int N);
 cudaError_t launch_proj_wgrad(const float* X, const float* Y, const float* fir, float* dW, int transposed_out, float beta,
                               int B, int L, int M, int N, float* part, cudaStream_t s);
+// k_layernorm.cu: residual add + LayerNorm (block glue)
+int ln_partials(long long rows);                     // CTAs (= rows of the dw/db partial scratch) the kernels use for `rows`
+cudaError_t launch_add_ln_fwd(const ln::FwdArgs& a, cudaStream_t s);
+cudaError_t launch_add_ln_bwd(ln::BwdArgs a, float* dw, float* db, cudaStream_t s);
 // k_convert.cu: reference filter-spectrum convention (rfft(k, fft_size), natural order) <-> packed spectrum
 cudaError_t launch_rfft_to_packed(const float2* X, float2* Z, int H, int logM, int logM1, cudaStream_t s);
 cudaError_t launch_packed_to_rfft(const float2* Z, float2* X, int H, int logM, int logM1, float scale, cudaStream_t s);

@@ -510,3 +510,65 @@ def side_stream(device):
         s = torch.cuda.Stream(device=device)
         _side_streams[key] = s
     return s
+
+
+# ------------------------------------------------------------------------------------------ block glue: add + LayerNorm
+_ln_scratch = {}
+
+
+class AddLayerNormFn(torch.autograd.Function):
+    """(y, res_out) = (LayerNorm(x + res) * w + b, x + res) in one pass over HBM (csrc/layernorm.cuh), fp32.
+
+    The pre-norm step of the Block that wraps the mixer (flash-attention/flash_attn/modules/block.py:111-148; with
+    fused_dropout_add_ln it is flash_attn.ops.layer_norm.dropout_add_layer_norm(prenorm=True, residual_in_fp32=True),
+    dropout p = 0).  ``res`` may be None (first block): res_out is then a copy of x."""
+
+    @staticmethod
+    def forward(ctx, x, res, w, b, eps):
+        _need_cuda(x, res, w, b)
+        if not x.is_contiguous() or (res is not None and (not res.is_contiguous() or res.shape != x.shape)):
+            raise _lib.HyenaB200Error("add_layer_norm: x and res must be contiguous and of the same shape")
+        D = x.shape[-1]
+        if w.numel() != D or (b is not None and b.numel() != D):
+            raise _lib.HyenaB200Error(f"add_layer_norm: weight / bias must have {D} elements")
+        rows = x.numel() // D
+        y = torch.empty_like(x)
+        res_out = torch.empty_like(x)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        w = w.contiguous()
+        b = b.contiguous() if b is not None else None
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().hyena_b200_add_layernorm_fwd(
+                _ptr(x), _ptr(res), _ptr(w), _ptr(b), float(eps), _ptr(res_out), _ptr(y),
+                _ptr(mean), _ptr(rstd), rows, D, _stream()))
+        ctx.save_for_backward(res_out, w, mean, rstd)
+        ctx.has_res, ctx.has_b, ctx.D, ctx.rows = res is not None, b is not None, D, rows
+        return y, res_out
+
+    @staticmethod
+    def backward(ctx, dy, dres):
+        r, w, mean, rstd = ctx.saved_tensors
+        D, rows = ctx.D, ctx.rows
+        dy = dy.contiguous()
+        dres = dres.contiguous() if dres is not None else None
+        _need_cuda(dy, dres)
+        dx = torch.empty_like(r)
+        dw = torch.empty(D, dtype=torch.float32, device=r.device)
+        db = torch.empty(D, dtype=torch.float32, device=r.device) if ctx.has_b else None
+        need = int(_lib.lib().hyena_b200_add_layernorm_scratch_bytes(rows, D))
+        key = (r.device.index if r.device.index is not None else torch.cuda.current_device(), _stream())
+        sc = _ln_scratch.get(key)
+        if sc is None or sc.numel() < need:
+            sc = torch.empty(need, dtype=torch.uint8, device=r.device)
+            _ln_scratch[key] = sc
+        with torch.cuda.device(r.device):
+            _lib.check(_lib.lib().hyena_b200_add_layernorm_bwd(
+                _ptr(dy), _ptr(dres), _ptr(r), _ptr(w), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(dw), _ptr(db), rows, D,
+                _ptr(sc), sc.numel(), _stream()))
+        # the gradient of x and of the incoming residual are the same tensor values
+        return dx, (dx if ctx.has_res else None), dw.reshape(w.shape), db, None
+
+
+def add_layer_norm(x, res, weight, bias, eps):
+    return AddLayerNormFn.apply(x, res, weight, bias, eps)

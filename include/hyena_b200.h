@@ -196,6 +196,22 @@ HY_API int hyena_b200_gemm(int transa, int transb, int m, int n, int k, float al
                            int ldc, long long strideC, int batch, const float* bias, int emulate, void* workspace,
                            size_t workspace_bytes, void* stream);
 
+/* ---- block glue: residual add + LayerNorm ---------------------------------------
+ * replaces the dropout(p=0) -> add -> LayerNorm step of the pre-norm Block that wraps the mixer
+ * (flash-attention/flash_attn/modules/block.py:111-148; with fused_dropout_add_ln it is
+ * flash_attn.ops.layer_norm.dropout_add_layer_norm(..., prenorm=True, residual_in_fp32=True)):
+ *   res_out = x + res (res may be NULL: first block, res_out may then be NULL too)
+ *   y = (res_out - mean) * rstd * w + b      per row of D features, fp32; mean / rstd (rows) are saved for the backward
+ * bwd: dy = grad of y, dres = grad arriving on res_out (may be NULL), r = res_out of the forward (x itself when no
+ *   residual was added).  dx (rows, D) is the gradient of x AND of res; dw / db (D) are overwritten (db may be NULL).
+ *   scratch: hyena_b200_add_layernorm_scratch_bytes(rows, D) bytes of per-CTA partial sums (deterministic reduction). */
+HY_API size_t hyena_b200_add_layernorm_scratch_bytes(long long rows, int D);
+HY_API int hyena_b200_add_layernorm_fwd(const float* x, const float* res, const float* w, const float* b, float eps,
+                                 float* res_out, float* y, float* mean, float* rstd, long long rows, int D, void* stream);
+HY_API int hyena_b200_add_layernorm_bwd(const float* dy, const float* dres, const float* r, const float* w, const float* mean,
+                                 const float* rstd, float* dx, float* dw, float* db, long long rows, int D, void* scratch,
+                                 size_t scratch_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,3 +65,25 @@ def test_module_rejects_options_outside_the_hot_path():
     assert isinstance(op.filter_fn.pos_emb.z, __import__("torch").nn.Parameter)     # class default lr_pos_emb=1e-5
     op0 = H.HyenaOperator(8, 64, emb_dim=3, lr_pos_emb=0.0)
     assert "filter_fn.pos_emb.z" in dict(op0.named_buffers())
+
+
+def test_block_glue_option_guards_and_state_dict_keys():
+    """Block / Backbone mirrors: options outside the path raise at construction; the parameter names
+    are the reference's (flash_attn Block: mixer / norm1 / mlp / norm2; LMBackbone: layers / ln_f)."""
+    from functools import partial
+    import torch
+    import hyena_dna_b200 as H
+    mixer = partial(H.HyenaOperator, l_max=64, emb_dim=5)
+    for kw in ({"prenorm": False}, {"resid_dropout1": 0.1}, {"drop_path2": 0.2}, {"sequence_parallel": True},
+               {"return_residual": True}):
+        with pytest.raises(H.HyenaB200Error):
+            H.Block(16, mixer_cls=mixer, **kw)
+    with pytest.raises(H.HyenaB200Error):
+        H.Block(16, mixer_cls=mixer, norm_cls=torch.nn.BatchNorm1d)
+    m = H.Backbone(16, 2, mixer, mlp_cls=None)
+    keys = set(m.state_dict().keys())
+    assert {"layers.0.norm1.weight", "layers.1.norm1.bias", "ln_f.weight", "layers.0.mixer.in_proj.weight",
+            "layers.1.mixer.filter_fn.implicit_filter.5.freq"} <= keys
+    assert not any(".norm2." in k for k in keys)          # mlp = Identity: no second norm, as in the reference
+    with pytest.raises(H.HyenaB200Error):                  # no CPU fallback
+        m(torch.zeros(1, 8, 16))
