@@ -49,6 +49,42 @@ __host__ __device__ constexpr size_t wimg_floats(int D) { return 4 * (size_t)kIm
 __device__ __noinline__ float sin_ni(float x) { return sinf(x); }
 __device__ __noinline__ float cos_ni(float x) { return cosf(x); }
 
+// Inline sin / cos for the epilogues: three-term Cody-Waite reduction by pi/2 (FMA) + the classic degree-7 / degree-8 minimax
+// polynomials on [-pi/4, pi/4], branch free.  <= 1.5 ulp for |x| <= 1e3 and <= 7e-8 absolute everywhere below the guard (checked
+// against fp64 over 1e7 arguments; libm's fp32 sin has the same absolute error) -- the accuracy class of sinf / torch.sin, which the
+// reference uses (hyena.py:105).  ~22 instructions with no call: the 16-32 evaluations of an epilogue are independent, so they
+// overlap (the out-of-line sinf serialised them: one ~120-cycle dependent chain per call, 0.5 instructions per scheduler-cycle).
+// Arguments here are freq * pre-activation (|x| <~ 1e2); beyond the guard the library function runs.
+__device__ __forceinline__ void sincos_core(float x, float& sn, float& cs, int& q) {
+  const float fq = rintf(x * 0.636619772367581343f);
+  q = (int)fq;
+  float r = fmaf(fq, -1.5707963705062866f, x);
+  r = fmaf(fq, 4.371138828673793e-08f, r);
+  r = fmaf(fq, 1.7763568394002505e-15f, r);
+  const float s = r * r;
+  float ps = fmaf(-1.95152959e-4f, s, 8.33216087e-3f);
+  ps = fmaf(ps, s, -1.66666546e-1f);
+  sn = fmaf(ps, s * r, r);
+  float pc = fmaf(2.44331571e-5f, s, -1.38873163e-3f);
+  pc = fmaf(pc, s, 4.16666457e-2f);
+  pc = fmaf(pc, s, -0.5f);
+  cs = fmaf(pc, s, 1.0f);
+}
+__device__ __forceinline__ float sin_acc(float x) {
+  if (fabsf(x) > 30000.f) return sin_ni(x);
+  float sn, cs; int q;
+  sincos_core(x, sn, cs, q);
+  const float v = (q & 1) ? cs : sn;
+  return (q & 2) ? -v : v;
+}
+__device__ __forceinline__ float cos_acc(float x) {
+  if (fabsf(x) > 30000.f) return cos_ni(x);
+  float sn, cs; int q;
+  sincos_core(x, sn, cs, q);
+  const float v = (q & 1) ? sn : cs;
+  return ((q + 1) & 2) ? -v : v;
+}
+
 // D[128 x N] = A * B^T as 3xTF32: 24 MMAs of K = 8, issued by the calling (single) thread.  The tensor core adds into
 // its accumulator with truncation, so a chain of n MMAs biases the sum by ~n 2^-24 towards zero (measured: the filter came
 // out 6x less accurate than the reference's fp32 path with all 24 products chained into one accumulator).  Hence two
@@ -203,7 +239,7 @@ filter_tc_fwd_kernel(const FilterParams P, const float* __restrict__ wimg, float
         float acc = b0s[i];
 #pragma unroll
         for (int e = 0; e < kMaxE; ++e) acc = fmaf(W0s[i * 16 + e], z[e], acc);
-        a[j] = sin_ni(frs[i] * acc);
+        a[j] = sin_acc(frs[i] * acc);
       }
       store_row_split<16>(smem, row, part * 16, a);
     }
@@ -224,7 +260,7 @@ filter_tc_fwd_kernel(const FilterParams P, const float* __restrict__ wimg, float
       float a[16];
       ld_acc16(lane_addr + part * 16, a);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) a[j] = sin_ni(frs[part * 16 + j] * (a[j] + bs[part * 16 + j]));
+      for (int j = 0; j < 16; ++j) a[j] = sin_acc(frs[part * 16 + j] * (a[j] + bs[part * 16 + j]));
       store_row_split<16>(smem, row, part * 16, a);        // the MMAs that read the A images have completed
       fence_before_sync();
       fence_async_smem();
@@ -266,6 +302,175 @@ filter_tc_fwd_kernel(const FilterParams P, const float* __restrict__ wimg, float
   __syncthreads();
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- forward, TS form
+// Round-2 form of the forward kernel (D <= 256; the kernel above stays for wider models):
+//   * the activations of a layer are the A operand IN TENSOR MEMORY: the thread that owns a position writes its
+//     (hi, lo) halves with tcgen05.st straight from the registers of the previous epilogue (TMEM lane = position,
+//     column = feature is exactly the A layout of an M = 128 MMA) -- no operand images built by the CUDA cores in
+//     shared memory, no bank conflicts, and 64 KB of shared memory back;
+//   * with that space ALL weight images (W1, W2, both halves of W3: 192 KB) stay resident for the whole kernel;
+//   * two tiles are in flight per CTA: warps 0-7 and 8-15 are two independent groups, each with its own half of
+//     tensor memory (accumulator 128 columns + A operand 2 x 64 columns), its own issuing thread, mbarrier and named
+//     barrier, working on alternate tiles -- one group's MMAs run under the other group's sin / exp epilogue (the
+//     single-tile kernel issued 0.51 instructions per scheduler-cycle with the tensor pipe 12 % busy);
+//   * one accumulator per layer, the 16 correction MMAs (lo*hi, hi*lo) first and the 8 hi*hi MMAs last, so that only
+//     those eight truncate at full scale (same accuracy as a separate correction accumulator, half the columns).
+constexpr uint32_t k2OffW3 = 65536;                               // after the W1 / W2 images (hi, lo each)
+__host__ __device__ constexpr size_t fwd2_smem_bytes(int D) { return 65536 + (size_t)((D + 127) / 128) * 65536 + kMiscFloats * 4 + 32; }
+
+__device__ __forceinline__ void issue_layer_ts(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                               int N, uint32_t mbar) {
+  const uint32_t idesc = make_idesc(N);
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {                   // lo*hi, hi*lo, then hi*hi
+    const uint32_t a = (pass == 0) ? a_lo : a_hi;
+    const uint32_t b = (pass == 1) ? b_lo : b_hi;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+      mma_tf32_ts(tmem_d, a + 8 * ks, make_desc(b + ks * 2 * kLBO), idesc, (ks > 0 || pass > 0) ? 1u : 0u);
+  }
+  mma_commit(mbar);
+}
+
+__device__ __forceinline__ void split_store32(uint32_t taddr_hi, uint32_t taddr_lo, const float (&a)[32]) {
+  uint32_t hi[32], lo[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float h, l;
+    split_tf32(a[j], h, l);
+    hi[j] = __float_as_uint(h); lo[j] = __float_as_uint(l);
+  }
+  tmem_st32(taddr_hi, hi);
+  tmem_st32(taddr_lo, lo);
+  tmem_wait_st();
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+filter_tc_fwd2_kernel(const FilterParams P, const float* __restrict__ wimg, float* __restrict__ kout, int ntiles) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int nh = (P.D + 127) / 128;                       // 1 or 2 (launcher)
+  float* misc = reinterpret_cast<float*>(smem + k2OffW3 + (size_t)nh * 65536);
+  float* W0s = misc;                    // [64][16]
+  float* b0s = misc + 64 * 16;
+  float* b1s = b0s + 64;
+  float* b2s = b1s + 64;
+  float* frs = b2s + 64;
+  uint64_t* mbar_p = reinterpret_cast<uint64_t*>(frs + 64);        // two barriers, one per group
+  uint32_t* tmem_p = reinterpret_cast<uint32_t*>(mbar_p + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = warp >> 3;                              // tile group of this warp
+  const int quad = warp & 3;                              // TMEM lane quadrant this warp may access
+  const int half = (warp >> 2) & 1;                       // which half of the columns
+  const int row = 32 * quad + lane;                       // position inside the tile == TMEM lane
+  const bool issuer = (tid & 255) == 0;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t mbar = smem_u32(mbar_p + grp);
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_p)), "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) { mbar_init(smem_u32(mbar_p), 1); mbar_init(smem_u32(mbar_p + 1), 1); }
+  {
+    const int pieces = (int)((65536 + (size_t)nh * 65536) / 16);   // all weight images, 16 bytes per cp.async
+    for (int i = tid; i < pieces; i += kThreads) cp_async16(smem + 16 * (size_t)i, wimg + 4 * (size_t)i, true);
+  }
+  for (int i = tid; i < 64 * 16; i += kThreads) {
+    const int r = i / 16, e = i % 16;
+    W0s[i] = (e < P.E) ? __ldg(P.W0 + r * P.E + e) : 0.f;
+  }
+  if (tid < 64) {
+    b0s[tid] = __ldg(P.b0 + tid); b1s[tid] = __ldg(P.b1 + tid); b2s[tid] = __ldg(P.b2 + tid);
+    frs[tid] = __ldg(P.freq + tid);
+  }
+  cp_async_wait_all();
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t gbase = *tmem_p + (uint32_t)grp * 256u;           // this group's columns: acc [0,128) A hi [128,192) lo [192,256)
+  const uint32_t lane_addr = gbase + ((uint32_t)(32 * quad) << 16);
+  const uint32_t a_hi = gbase + 128, a_lo = gbase + 192;
+  auto group_sync = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(1 + grp) : "memory"); };
+  uint32_t phase = 0;
+
+  for (int tile = 2 * blockIdx.x + grp; tile < ntiles; tile += 2 * gridDim.x) {
+    const int t = tile * kTileM + row;
+    const bool tv = t < P.L;
+    // ---- layer 0 on the CUDA cores: a1 = sin(f * (W0 z + b0)), 32 features per thread
+    {
+      float z[kMaxE];
+#pragma unroll
+      for (int e = 0; e < kMaxE; ++e) z[e] = (tv && e < P.E) ? __ldg(P.z + (size_t)t * P.z_stride + e) : 0.f;
+      float a[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int i = half * 32 + j;
+        float acc = b0s[i];
+#pragma unroll
+        for (int e = 0; e < kMaxE; ++e) acc = fmaf(W0s[i * 16 + e], z[e], acc);
+        a[j] = sin_acc(frs[i] * acc);
+      }
+      split_store32(lane_addr + 128 + half * 32, lane_addr + 192 + half * 32, a);
+    }
+    fence_before_sync();
+    group_sync();
+    // ---- layers 1 and 2 on the tensor cores
+#pragma unroll
+    for (int layer = 0; layer < 2; ++layer) {
+      if (issuer) {
+        fence_after_sync();
+        issue_layer_ts(gbase, a_hi, a_lo, sbase + (layer ? 32768u : 0u), sbase + (layer ? 49152u : 16384u), 64, mbar);
+      }
+      mbar_wait_u(mbar, phase);
+      phase ^= 1;
+      fence_after_sync();
+      const float* bs = layer ? b2s : b1s;
+      float a[32];
+      tmem_ld32(lane_addr + half * 32, a);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) a[j] = sin_acc(frs[half * 32 + j] * (a[j] + bs[half * 32 + j]));
+      split_store32(lane_addr + 128 + half * 32, lane_addr + 192 + half * 32, a);   // the MMAs that read A have completed
+      fence_before_sync();
+      group_sync();
+    }
+    // ---- output layer, 128 channels at a time, modulation in the epilogue
+    const float tpos = tv ? __ldg(P.t + t) : 0.f;
+    for (int h = 0; h < nh; ++h) {
+      if (issuer) {
+        fence_after_sync();
+        issue_layer_ts(gbase, a_hi, a_lo, sbase + k2OffW3 + h * 65536u, sbase + k2OffW3 + h * 65536u + 32768u, 128, mbar);
+      }
+      mbar_wait_u(mbar, phase);
+      phase ^= 1;
+      fence_after_sync();
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        float v[32];
+        tmem_ld32(lane_addr + half * 64 + c0, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int c = h * 128 + half * 64 + c0 + j;
+          if (c < P.D && tv) {
+            float x = v[j];
+            if (P.modulate) x *= (expf(-tpos * fabsf(__ldg(P.deltas + c))) + P.shift);
+            kout[(size_t)c * P.L + t] = x;
+          }
+        }
+      }
+      fence_before_sync();
+      group_sync();                                      // accumulator (and, after the last half, the A operand) is free
+    }
+  }
+
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_p), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -387,7 +592,7 @@ filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const
 #pragma unroll
         for (int e = 0; e < kMaxE; ++e) acc = fmaf(W0s[i * 16 + e], z[e], acc);
         pre1[j] = acc;
-        a[j] = sin_ni(fr[j] * acc);
+        a[j] = sin_acc(fr[j] * acc);
       }
       store_row_split<16>(smem, row, part * 16, a);
       if (tv) store16(out + 0 * arr, P.L, a);
@@ -402,7 +607,7 @@ filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const
     fence_after_sync();
     ld_acc16(lane_addr + part * 16, pre2);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { pre2[j] += b1s[part * 16 + j]; a[j] = sin_ni(fr[j] * pre2[j]); }
+    for (int j = 0; j < 16; ++j) { pre2[j] += b1s[part * 16 + j]; a[j] = sin_acc(fr[j] * pre2[j]); }
     store_row_split<16>(smem, row, part * 16, a);
     if (tv) store16(out + 1 * arr, P.L, a);
     fence_before_sync();
@@ -416,7 +621,7 @@ filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const
     fence_after_sync();
     ld_acc16(lane_addr + part * 16, pre3);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { pre3[j] += b2s[part * 16 + j]; a[j] = sin_ni(fr[j] * pre3[j]); }
+    for (int j = 0; j < 16; ++j) { pre3[j] += b2s[part * 16 + j]; a[j] = sin_acc(fr[j] * pre3[j]); }
     if (tv) store16(out + 2 * arr, P.L, a);
     fence_before_sync();
 
@@ -476,7 +681,7 @@ filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const
     ld_acc16(lane_addr + part * 16, da);
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const float cs = cos_ni(fr[j] * pre3[j]);
+      const float cs = cos_acc(fr[j] * pre3[j]);
       const float g = da[j] * cs;
       X[j] = g * pre3[j];
       a[j] = g * fr[j];
@@ -497,7 +702,7 @@ filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const
     ld_acc16(lane_addr + part * 16, da);
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const float cs = cos_ni(fr[j] * pre2[j]);
+      const float cs = cos_acc(fr[j] * pre2[j]);
       const float g = da[j] * cs;
       X[j] = fmaf(g, pre2[j], X[j]);
       a[j] = g * fr[j];
@@ -517,7 +722,7 @@ filter_tc_bwd_kernel(const FilterParams P, const float* __restrict__ wimg, const
     ld_acc16(lane_addr + part * 16, da);
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const float cs = cos_ni(fr[j] * pre1[j]);
+      const float cs = cos_acc(fr[j] * pre1[j]);
       const float g = da[j] * cs;
       X[j] = fmaf(g, pre1[j], X[j]);
       a[j] = g * fr[j];
