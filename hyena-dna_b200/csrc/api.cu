@@ -4,7 +4,9 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <utility>
 #include <vector>
 
 #include "../../include/hyena_b200.h"
@@ -337,21 +339,24 @@ HY_API size_t hyena_b200_workspace_bytes(int B, int D, int L, int backward) {
   return hyena_b200_workspace_min_bytes(B, D, L, backward) * (size_t)nch;
 }
 
-// tensor-core filter path: per-device scratch for the tf32 hi/lo weight images (grow-only)
+// tensor-core filter path: scratch for the tf32 hi/lo weight images (~0.3 MB, grow-only), one per (device, stream): two
+// operators driven from different streams never share it (the prep kernel of one would overwrite the images the other's
+// tcgen05 kernel is still reading)
 static int get_wimg(int D, cudaStream_t stream, float** out) {
   int dev = -1;
   HY_CUDA(cudaGetDevice(&dev));
   HY_CHECK(dev >= 0 && dev < 64, "unsupported device ordinal %d", dev);
   std::lock_guard<std::mutex> lk(g_mu);
-  static float* bufs[64] = {nullptr};
-  static size_t sizes[64] = {0};
+  struct Buf { float* p = nullptr; size_t n = 0; };
+  static std::map<std::pair<int, cudaStream_t>, Buf> bufs;
+  Buf& b = bufs[std::make_pair(dev, stream)];
   const size_t need = filter_tc_wimg_bytes(D);
-  if (sizes[dev] < need) {
-    if (bufs[dev]) { HY_CUDA(cudaStreamSynchronize(stream)); HY_CUDA(cudaFree(bufs[dev])); }
-    HY_CUDA(cudaMalloc(&bufs[dev], need));
-    sizes[dev] = need;
+  if (b.n < need) {
+    if (b.p) { HY_CUDA(cudaStreamSynchronize(stream)); HY_CUDA(cudaFree(b.p)); b.p = nullptr; b.n = 0; }
+    HY_CUDA(cudaMalloc(&b.p, need));
+    b.n = need;
   }
-  *out = bufs[dev];
+  *out = b.p;
   return 0;
 }
 

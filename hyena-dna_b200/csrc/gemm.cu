@@ -25,7 +25,7 @@ int api_fail(const char* fmt, ...);   // api.cu
 
 struct LtApi {
   void* so = nullptr;
-  cublasLtHandle_t handle = nullptr;
+  cublasLtHandle_t handles[64] = {nullptr};      // one per device, created on first use there
   size_t version = 0;
   decltype(&cublasLtCreate) Create;
   decltype(&cublasLtGetVersion) GetVersion;
@@ -75,10 +75,6 @@ static bool lt_load() {
     snprintf(g_lt_why, sizeof(g_lt_why), "cuBLASLt %zu has no BF16x9 fp32 emulation (need >= 12.9)", g_lt.version);
     return false;
   }
-  if (g_lt.Create(&g_lt.handle) != CUBLAS_STATUS_SUCCESS) {
-    snprintf(g_lt_why, sizeof(g_lt_why), "cublasLtCreate failed");
-    return false;
-  }
   g_lt.so = so;
   g_lt_state = 1;
   return true;
@@ -91,8 +87,17 @@ struct Plan {
   size_t ws = 0;
   bool ok = false;
 };
-using Key = std::tuple<int, int, int, int, int, int, int, int, int, long long, long long, long long, int, int>;
+// first element: device ordinal (heuristics / algos are per device)
+using Key = std::tuple<int, int, int, int, int, int, int, int, int, int, long long, long long, long long, int, int>;
 static std::map<Key, Plan> g_plans;
+
+static void plan_destroy(Plan& p) {
+  if (p.a) g_lt.LayoutDestroy(p.a);
+  if (p.b) g_lt.LayoutDestroy(p.b);
+  if (p.c) g_lt.LayoutDestroy(p.c);
+  if (p.desc) g_lt.DescDestroy(p.desc);
+  p = Plan();
+}
 
 }  // namespace hy
 
@@ -117,13 +122,24 @@ HY_API int hyena_b200_gemm(int transa, int transb, int m, int n, int k, float al
   if (!lt_load()) return api_fail("%s", g_lt_why);
   if (m < 1 || n < 1 || k < 1 || batch < 1 || !A || !B || !C) return api_fail("gemm: bad arguments");
   std::lock_guard<std::mutex> lk(g_lt_mu);
-  Key key{transa, transb, m, n, k, lda, ldb, ldc, batch, strideA, strideB, strideC, bias != nullptr, emulate};
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return api_fail("gemm: unsupported device ordinal %d", dev);
+  if (!g_lt.handles[dev] && g_lt.Create(&g_lt.handles[dev]) != CUBLAS_STATUS_SUCCESS) {
+    g_lt.handles[dev] = nullptr;
+    return api_fail("cublasLtCreate failed on device %d", dev);
+  }
+  cublasLtHandle_t handle = g_lt.handles[dev];
+  Key key{dev, transa, transb, m, n, k, lda, ldb, ldc, batch, strideA, strideB, strideC, bias != nullptr, emulate};
   Plan& p = g_plans[key];
-  if (!p.desc) {
+  if (!p.ok) {
+    plan_destroy(p);                       // a previous attempt may have left partial objects behind
     // emulate: 0 = plain fp32, 1 = BF16x9 emulation (fp32-level accuracy), 2 = TF32 (opt-in: torch allow_tf32)
     const cublasComputeType_t ct = emulate == 1 ? CUBLAS_COMPUTE_32F_EMULATED_16BFX9
                                    : emulate == 2 ? CUBLAS_COMPUTE_32F_FAST_TF32 : CUBLAS_COMPUTE_32F;
-    if (g_lt.DescCreate(&p.desc, ct, CUDA_R_32F) != CUBLAS_STATUS_SUCCESS) return api_fail("cublasLtMatmulDescCreate failed");
+    if (g_lt.DescCreate(&p.desc, ct, CUDA_R_32F) != CUBLAS_STATUS_SUCCESS) {
+      g_plans.erase(key);
+      return api_fail("cublasLtMatmulDescCreate failed");
+    }
     cublasOperation_t ta = transa ? CUBLAS_OP_T : CUBLAS_OP_N, tb = transb ? CUBLAS_OP_T : CUBLAS_OP_N;
     g_lt.DescSet(p.desc, CUBLASLT_MATMUL_DESC_TRANSA, &ta, sizeof(ta));
     g_lt.DescSet(p.desc, CUBLASLT_MATMUL_DESC_TRANSB, &tb, sizeof(tb));
@@ -140,8 +156,11 @@ HY_API int hyena_b200_gemm(int transa, int transb, int m, int n, int k, float al
       return true;
     };
     if (!mk(&p.a, transa ? k : m, transa ? m : k, lda, strideA) || !mk(&p.b, transb ? n : k, transb ? k : n, ldb, strideB) ||
-        !mk(&p.c, m, n, ldc, strideC))
+        !mk(&p.c, m, n, ldc, strideC)) {
+      plan_destroy(p);
+      g_plans.erase(key);
       return api_fail("cublasLtMatrixLayoutCreate failed");
+    }
     cublasLtMatmulPreference_t pref = nullptr;
     g_lt.PrefCreate(&pref);
     size_t wsb = workspace ? workspace_bytes : 0;
@@ -152,9 +171,10 @@ HY_API int hyena_b200_gemm(int transa, int transb, int m, int n, int k, float al
     }
     cublasLtMatmulHeuristicResult_t res;
     int found = 0;
-    cublasStatus_t st = g_lt.Heuristic(g_lt.handle, p.desc, p.a, p.b, p.c, p.c, pref, 1, &res, &found);
+    cublasStatus_t st = g_lt.Heuristic(handle, p.desc, p.a, p.b, p.c, p.c, pref, 1, &res, &found);
     g_lt.PrefDestroy(pref);
     if (st != CUBLAS_STATUS_SUCCESS || found < 1) {
+      plan_destroy(p);
       g_plans.erase(key);
       return api_fail("cublasLt heuristic found no algorithm (status %d) for m=%d n=%d k=%d emulate=%d", (int)st, m, n, k, emulate);
     }
@@ -167,7 +187,7 @@ HY_API int hyena_b200_gemm(int transa, int transb, int m, int n, int k, float al
     g_lt.DescSet(p.desc, CUBLASLT_MATMUL_DESC_BIAS_POINTER, &bp, sizeof(bp));
   }
   if (p.ws > workspace_bytes) return api_fail("gemm workspace too small (%zu needed)", p.ws);
-  cublasStatus_t st = g_lt.Matmul(g_lt.handle, p.desc, &alpha, A, p.a, B, p.b, &beta, C, p.c, C, p.c, &p.algo, workspace,
+  cublasStatus_t st = g_lt.Matmul(handle, p.desc, &alpha, A, p.a, B, p.b, &beta, C, p.c, C, p.c, &p.algo, workspace,
                                   p.ws, (cudaStream_t)stream);
   if (st != CUBLAS_STATUS_SUCCESS) return api_fail("cublasLtMatmul failed with status %d", (int)st);
   return 0;

@@ -266,9 +266,9 @@ class _OutProj(torch.autograd.Function):
                 # dW^T (C x Do, ld C) = sum_b Ypre_b (C x L; stored (L x C, ld L) -> op T) dY_b (L x Do; stored (Do x L) -> op T)
                 for b in range(B):
                     ops.gemm(1, 1, C, Do, L, y_pre[b], L, 0, dy[b], Do, 0, dW, C, 0, batch=1, beta=0.0 if b == 0 else 1.0)
-                if ctx.has_bias and ctx.needs_input_grad[2]:
-                    db = dy.sum((0, 1))
-        elif ctx.has_bias and ctx.needs_input_grad[2]:
+        # db on the caller's stream: a tensor allocated inside the side-stream context and consumed by autograd on the main
+        # stream could be handed back to side-stream work by the caching allocator while main-stream readers are pending
+        if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.sum((0, 1))
         if ctx.needs_input_grad[0]:
             d_pre = torch.empty_like(y_pre)
