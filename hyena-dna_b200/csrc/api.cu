@@ -313,7 +313,7 @@ HY_API const char* hyena_b200_kind_name(int kind) {
       "row_pass<filter>", "row_pass<conv_fwd>", "row_pass<conv_bwd>",
       "filter_fwd", "filter_bwd", "short_conv_bwd", "twiddle_init", "filter_tc_prep", "filter_tc_fwd", "filter_tc_bwd", "filter_tc_red", "fused_conv_fwd",
       "spectrum_convert", "proj_prep", "proj_gemm", "proj_wgrad",
-      "conv_fwd<pipelined>", "conv_bwd<pipelined>", "filter_spectrum<pipelined>", "add_layer_norm"};
+      "conv_fwd<pipelined>", "conv_bwd<pipelined>", "filter_spectrum<pipelined>", "add_layer_norm", "filter_extra"};
   return (kind >= 0 && kind < K_COUNT) ? names[kind] : "?";
 }
 
@@ -714,6 +714,28 @@ HY_API int hyena_b200_fftconv_bwd(const float* dout, const float* u, const float
     a.B = 1; a.out = dk;
     HY_CUDA(launch_col_inv(INV_DK, a, n, s));
   }
+  return 0;
+}
+
+/* d deltas (D) = gradient of k = h * (exp(-t |deltas|) + shift) w.r.t. deltas (ExponentialModulation with modulation_lr != 0,
+ * hyena.py:145-155); k is the filter the forward produced, dk its gradient, both (D, L); t (L). */
+HY_API int hyena_b200_filter_ddelta(const float* dk, const float* k, const float* t, const float* deltas, float shift, int D,
+                             int L, float* ddelta, void* stream) {
+  HY_CHECK(D >= 1 && L >= 1 && dk && k && t && deltas && ddelta, "filter_ddelta: bad arguments");
+  HY_CUDA(launch_filter_ddelta(dk, k, t, deltas, shift, D, L, ddelta, (cudaStream_t)stream));
+  return 0;
+}
+
+/* normalized=True (hyena.py:235-236): out[c][t] = k[c][t] / norm[t], norm[t] = sum_c |k[c][t]|;  bwd: dk from dout, out, norm */
+HY_API int hyena_b200_filter_l1norm_fwd(const float* k, float* out, float* norm, int D, int L, void* stream) {
+  HY_CHECK(D >= 1 && L >= 1 && k && out && norm, "filter_l1norm_fwd: bad arguments");
+  HY_CUDA(launch_l1norm_fwd(k, out, norm, D, L, (cudaStream_t)stream));
+  return 0;
+}
+HY_API int hyena_b200_filter_l1norm_bwd(const float* dout, const float* out, const float* norm, float* dk, int D, int L,
+                                 void* stream) {
+  HY_CHECK(D >= 1 && L >= 1 && dout && out && norm && dk, "filter_l1norm_bwd: bad arguments");
+  HY_CUDA(launch_l1norm_bwd(dout, out, norm, dk, D, L, (cudaStream_t)stream));
   return 0;
 }
 

@@ -16,7 +16,8 @@ enum Kind {
   K_FILTER_TC_BWD = 18, K_FILTER_TC_RED = 19, K_FUSED_FWD = 20, K_CONVERT = 21, K_PROJ_PREP = 22, K_PROJ_GEMM = 23, K_PROJ_WGRAD = 24,
   K_PIPE_FWD = 25, K_PIPE_BWD = 26, K_PIPE_FILTER = 27,   // whole pipelined calls (api.cu PipeRun): kernels of different groups overlap
   K_ADD_LN = 28,            // residual add + LayerNorm (block glue, layernorm.cuh)
-  K_COUNT = 29
+  K_FILTER_EXTRA = 29,      // deltas gradient / channel L1 normalisation (filter_extra.cuh; non-default filter options)
+  K_COUNT = 30
 };
 void prof_begin(int kind, cudaStream_t s);     // api.cu: records an event when profiling is on
 void prof_end(int kind, cudaStream_t s);       // api.cu: records an event when profiling is on; counts the launch
@@ -43,6 +44,11 @@ cudaError_t launch_proj_gemm(const float* act, int act_layout, const float* W, i
 size_t proj_wgrad_scratch_bytes(int M, int N);
 cudaError_t launch_proj_wgrad(const float* X, const float* Y, const float* fir, float* dW, int transposed_out, float beta,
                               int B, int L, int M, int N, float* part, cudaStream_t s);
+// k_filter.cu: filter_extra.cuh
+cudaError_t launch_filter_ddelta(const float* dk, const float* k, const float* t, const float* deltas, float shift, int D,
+                                 int L, float* ddelta, cudaStream_t s);
+cudaError_t launch_l1norm_fwd(const float* k, float* out, float* norm, int D, int L, cudaStream_t s);
+cudaError_t launch_l1norm_bwd(const float* dout, const float* out, const float* norm, float* dk, int D, int L, cudaStream_t s);
 // k_layernorm.cu: residual add + LayerNorm (block glue)
 int ln_partials(long long rows);                     // CTAs (= rows of the dw/db partial scratch) the kernels use for `rows`
 cudaError_t launch_add_ln_fwd(const ln::FwdArgs& a, cudaStream_t s);

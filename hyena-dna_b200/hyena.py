@@ -86,8 +86,8 @@ class HyenaFilter(OptimModule):
                  dropout=0.0, w=1, wd=0, bias=True, num_inner_mlps=2, linear_mixer=False, modulate=True,
                  normalized=False, bidirectional=False, **kwargs):
         super().__init__()
-        if linear_mixer or normalized or bidirectional or num_inner_mlps != 2 or dropout != 0.0:
-            raise HyenaB200Error("HyenaFilter: linear_mixer / normalized / bidirectional / num_inner_mlps != 2 / "
+        if linear_mixer or num_inner_mlps != 2 or dropout != 0.0:
+            raise HyenaB200Error("HyenaFilter: linear_mixer / num_inner_mlps != 2 / "
                                  "dropout are outside the sm_100a hot path (no fallback)")
         if order != 64:
             raise HyenaB200Error(f"HyenaFilter: filter order {order} not supported by the fused kernel (64 only)")
@@ -132,13 +132,30 @@ class HyenaFilter(OptimModule):
         k = ops.HyenaFilterFn.apply(*args, float(self.modulation.shift), bool(self.modulate), int(L), cached)
         if getattr(self, "cache_filter", False) and cached is None:
             self._filter_cache = (key, k.detach())
+        if self.normalized:                     # hyena.py:235-236: L1 norm over the channels of every position
+            k = ops.FilterL1NormFn.apply(k)
         return k
 
     def filter(self, L, *args, **kwargs):
         return self.filter_channel_major(L).transpose(0, 1).unsqueeze(0)
 
     def forward(self, x, L, k=None, bias=None, *args, **kwargs):
-        from .fftconv import fftconv_func
+        from .fftconv import fftconv_func, fftconv_ref
+        if self.bidirectional:                 # hyena.py:261: fftconv_ref(..., bidirectional=self.bidirectional)
+            if k is None:
+                k = self.filter_channel_major(L)
+            else:
+                k = k[0] if type(k) is tuple else k
+                if k.dim() == 3:
+                    k = k[0].transpose(0, 1)
+            b = self.bias if bias is None else bias
+            b = b if self.use_bias else 0 * b
+            if x.dim() == 5:
+                bb, h, v, zz, l = x.shape
+                x3 = x.permute(0, 3, 1, 2, 4).reshape(bb * zz, h * v, l)
+                y = fftconv_ref(x3, k, b.reshape(-1), None, gelu=False, bidirectional=True)
+                return y.reshape(bb, zz, h, v, l).permute(0, 2, 3, 1, 4).to(dtype=x.dtype)
+            return fftconv_ref(x, k, b.reshape(-1), None, gelu=False, bidirectional=True)
         if k is None:
             k = self.filter_channel_major(L)
         else:
@@ -335,7 +352,7 @@ class HyenaOperator(nn.Module):
             else:
                 kspec = ops.filter_spectrum(k.detach())
                 self._kspec_cache = (kkey, kspec)
-        if self.order > 2:
+        if self.order > 2 or self.filter_fn.bidirectional:
             y_pre = self._forward_chained(u, k, fb, l_filter)
         elif ops.proj_mode() == "tc" and l_filter == l and ops.fuse_fir():
             # one autograd node: in_proj GEMM + fused core; backward feeds ds straight into the projection GEMMs
@@ -368,8 +385,14 @@ class HyenaOperator(nn.Module):
         *x, v = uc.split(D, dim=1)
         kk = k.reshape(D, O1, l_filter)                                             # filter channels are ordered (v o): :408-412
         bb = fb.reshape(D, O1)
+        bidir = self.filter_fn.bidirectional
         for o, x_i in enumerate(reversed(x[1:])):
-            v = fftconv_func((v * x_i).contiguous(), kk[:, o].contiguous(), bb[:, o].contiguous(), gelu=False)
+            if bidir:
+                from .fftconv import fftconv_ref
+                v = fftconv_ref((v * x_i).contiguous(), kk[:, o].contiguous(), bb[:, o].contiguous(), None, gelu=False,
+                                bidirectional=True)
+            else:
+                v = fftconv_func((v * x_i).contiguous(), kk[:, o].contiguous(), bb[:, o].contiguous(), gelu=False)
         return (v * x[0]).contiguous()
 
     @property

@@ -134,18 +134,34 @@ class HyenaFilterFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, shift, modulate, L, cached=None):
-        ctx.save_for_backward(z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas)
         ctx.cfg = (shift, modulate, L)
         if cached is not None:                 # same inputs as the call that produced it (HyenaFilter.filter_channel_major)
-            return cached.detach()
-        return filter_forward(z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, shift, modulate, L)
+            k = cached.detach()
+        else:
+            k = filter_forward(z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, shift, modulate, L)
+        # trainable deltas (modulation_lr != 0): their gradient needs the filter itself
+        need_k = modulate and torch.is_tensor(deltas) and deltas.requires_grad
+        ctx.save_for_backward(z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, k if need_k else None)
+        return k
 
     @staticmethod
     def backward(ctx, dk):
-        z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas = ctx.saved_tensors
+        z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, ksaved = ctx.saved_tensors
         shift, modulate, L = ctx.cfg
+        ddelta = None
         if ctx.needs_input_grad[10]:
-            raise _lib.HyenaB200Error("gradients w.r.t. modulation deltas (modulation_lr != 0) are not implemented")
+            if not modulate or ksaved is None:
+                ddelta = torch.zeros_like(deltas)
+            else:                                      # ExponentialModulation with modulation_lr != 0 (hyena.py:145-155)
+                D = ksaved.shape[0]
+                dkc = dk.contiguous()
+                tt = (t[0, :L, 0] if t.dim() == 3 else t[:L]).contiguous()
+                dl = deltas.reshape(-1).contiguous()
+                dd = torch.empty(D, dtype=torch.float32, device=dk.device)
+                with torch.cuda.device(dk.device):
+                    _lib.check(_lib.lib().hyena_b200_filter_ddelta(_ptr(dkc), _ptr(ksaved), _ptr(tt), _ptr(dl), float(shift),
+                                                                    D, int(L), _ptr(dd), _stream()))
+                ddelta = dd.reshape(deltas.shape)
         need_dz = ctx.needs_input_grad[0]
         grads, dfreq, dz = filter_backward(z, t, W0, b0, W1, b1, W2, b2, W3, freq, deltas, shift, modulate, L,
                                            dk, need_dz)
@@ -153,7 +169,35 @@ class HyenaFilterFn(torch.autograd.Function):
         if need_dz:
             gz = torch.zeros_like(z)
             (gz[0, :L] if z.dim() == 3 else gz[:L]).copy_(dz)
-        return (gz, None, *grads, dfreq.reshape(freq.shape), None, None, None, None, None)
+        return (gz, None, *grads, dfreq.reshape(freq.shape), ddelta, None, None, None, None)
+
+
+class FilterL1NormFn(torch.autograd.Function):
+    """k (D, L) -> k / sum_c |k[c, t]|: HyenaFilter(normalized=True), hyena.py:235-236 (L1 norm over the channel dim of the
+    reference's (1, L, D) layout)."""
+
+    @staticmethod
+    def forward(ctx, k):
+        _need_cuda(k)
+        k = k.contiguous()
+        D, L = k.shape
+        out = torch.empty_like(k)
+        norm = torch.empty(L, dtype=torch.float32, device=k.device)
+        with torch.cuda.device(k.device):
+            _lib.check(_lib.lib().hyena_b200_filter_l1norm_fwd(_ptr(k), _ptr(out), _ptr(norm), D, L, _stream()))
+        ctx.save_for_backward(out, norm)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        out, norm = ctx.saved_tensors
+        dout = dout.contiguous()
+        _need_cuda(dout)
+        D, L = out.shape
+        dk = torch.empty_like(out)
+        with torch.cuda.device(out.device):
+            _lib.check(_lib.lib().hyena_b200_filter_l1norm_bwd(_ptr(dout), _ptr(out), _ptr(norm), _ptr(dk), D, L, _stream()))
+        return dk
 
 
 # ------------------------------------------------------------------------------------------ spectrum / core

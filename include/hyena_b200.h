@@ -196,6 +196,17 @@ HY_API int hyena_b200_gemm(int transa, int transb, int m, int n, int k, float al
                            int ldc, long long strideC, int batch, const float* bias, int emulate, void* workspace,
                            size_t workspace_bytes, void* stream);
 
+/* ---- filter options outside the shipped configs -------------------------------------------------
+ * modulation_lr != 0 (hyena.py:145-150: deltas is a Parameter): d deltas (D) from the filter k (D, L) the forward produced and
+ * its gradient dk (D, L); t (L) = PositionalEmbedding.t.  Overwrites ddelta. */
+HY_API int hyena_b200_filter_ddelta(const float* dk, const float* k, const float* t, const float* deltas, float shift, int D,
+                             int L, float* ddelta, void* stream);
+/* normalized=True (hyena.py:235-236, L1 norm over the channel dim of (1, L, D)): out[c][t] = k[c][t] / norm[t],
+ * norm[t] = sum_c |k[c][t]| (L values, kept for the backward); bwd: dk = (dout - sign(out) * sum_c dout*out) / norm. */
+HY_API int hyena_b200_filter_l1norm_fwd(const float* k, float* out, float* norm, int D, int L, void* stream);
+HY_API int hyena_b200_filter_l1norm_bwd(const float* dout, const float* out, const float* norm, float* dk, int D, int L,
+                                 void* stream);
+
 /* ---- block glue: residual add + LayerNorm ---------------------------------------
  * replaces the dropout(p=0) -> add -> LayerNorm step of the pre-norm Block that wraps the mixer
  * (flash-attention/flash_attn/modules/block.py:111-148; with fused_dropout_add_ln it is

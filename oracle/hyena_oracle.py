@@ -106,13 +106,16 @@ def implicit_filter(z, P):
     return F.linear(h, P["filter_fn.implicit_filter.6.weight"])
 
 
-def hyena_filter(L, P, shift=0.0, modulate=True):
-    """k (1,L,D).  src/models/sequence/hyena.py:229-238 with :152-155 modulation."""
+def hyena_filter(L, P, shift=0.0, modulate=True, normalized=False):
+    """k (1,L,D).  src/models/sequence/hyena.py:229-238 with :152-155 modulation and the optional L1 normalisation over
+    the channel dim (:235-236)."""
     z = P["filter_fn.pos_emb.z"][:, :L]
     t = P["filter_fn.pos_emb.t"][:, :L]
     h = implicit_filter(z, P)
     if modulate:
         h = h * (torch.exp(-t * P["filter_fn.modulation.deltas"].abs()) + shift)
+    if normalized:
+        h = h / torch.norm(h, dim=-1, p=1, keepdim=True)
     return h
 
 
@@ -150,7 +153,7 @@ def short_filter(p, W, b, L):
     return F.conv1d(p, W, b, padding=W.shape[-1] - 1, groups=C)[..., :L]
 
 
-def hyena_operator(u, P, shift=0.0, modulate=True, return_intermediates=False):
+def hyena_operator(u, P, shift=0.0, modulate=True, return_intermediates=False, normalized=False):
     """HyenaOperator.forward for any order >= 2 (heads=1, blocks=1, activation=id, dropout=0); the order is read off
     in_proj.weight ((order+1)*D rows).
 
@@ -161,7 +164,7 @@ def hyena_operator(u, P, shift=0.0, modulate=True, return_intermediates=False):
     uc = short_filter(p, P["short_filter.weight"], P["short_filter.bias"], L)      # :394
     *x, v = uc.split(D, dim=1)                                                     # :404
     # filter channels are ordered (v o): channel = v * (order-1) + o                 :405-412
-    k = hyena_filter(L, P, shift, modulate)[0].transpose(0, 1).reshape(D, order - 1, L)
+    k = hyena_filter(L, P, shift, modulate, normalized)[0].transpose(0, 1).reshape(D, order - 1, L)
     bias = P["filter_fn.bias"].reshape(D, order - 1)
     g = c = None
     for o, x_i in enumerate(reversed(x[1:])):                                      # :414-423
@@ -174,13 +177,14 @@ def hyena_operator(u, P, shift=0.0, modulate=True, return_intermediates=False):
     return y
 
 
-def operator_fwd_bwd(u, P, dy, shift=0.0, grads_for=None):
-    """Forward + autograd backward; returns y, du and a dict of parameter grads."""
+def operator_fwd_bwd(u, P, dy, shift=0.0, grads_for=None, normalized=False):
+    """Forward + autograd backward; returns y, du and a dict of parameter grads (grads_for: names, e.g. to include
+    "filter_fn.modulation.deltas" when modulation_lr != 0)."""
     names = grads_for or [k for k in P if k not in ("filter_fn.pos_emb.z", "filter_fn.pos_emb.t",
                                                     "filter_fn.modulation.deltas")]
     Q = {k: (v.detach().clone().requires_grad_(k in names)) for k, v in P.items()}
     u = u.detach().clone().requires_grad_(True)
-    y = hyena_operator(u, Q, shift)
+    y = hyena_operator(u, Q, shift, normalized=normalized)
     y.backward(dy)
     return y.detach(), u.grad.detach(), {k: Q[k].grad.detach() for k in names}
 

@@ -29,6 +29,9 @@ CASES = {
     # order = 3: the shipped HyenaDNA layer default (configs/model/layer/hyena_dna.yaml:3), two chained recurrences
     "ref_order3_L256_D16": (2, 256, 16, 5, 10.0, 256, 0.02, 3),
     "ref_order3_L200_D8":  (1, 200, 8, 5, 10.0, 256, None, 3),
+    # filter options outside the shipped configs: L1-normalised filter (hyena.py:235-236) and trainable modulation deltas
+    # (modulation_lr != 0, hyena.py:145-150), with a non-zero shift
+    "ref_norm_modlr_L256_D16": (2, 256, 16, 5, 10.0, 256, 0.02, 2, {"normalized": True, "modulation_lr": 1e-3, "shift": 0.05}),
 }
 
 
@@ -52,15 +55,18 @@ def _shim():
 def build(case, which):
     B, L, D, E, w, l_max, init_std = CASES[case][:7]
     order = CASES[case][7] if len(CASES[case]) > 7 else 2
+    extra = dict(CASES[case][8]) if len(CASES[case]) > 8 else {}
     torch.manual_seed(1234)
     if which == "standalone":
         import standalone_hyenadna as S
-        op = S.HyenaOperator(D, l_max, order=order, filter_order=64, emb_dim=E, w=w, shift=0.0, lr_pos_emb=0.0)
+        kw = {"shift": 0.0}
+        kw.update(extra)
+        op = S.HyenaOperator(D, l_max, order=order, filter_order=64, emb_dim=E, w=w, lr_pos_emb=0.0, **kw)
         init = S._init_weights
     else:
         from src.models.sequence.hyena import HyenaOperator
         op = HyenaOperator(D, l_max, order=order, filter_order=64, emb_dim=E, w=w, lr_pos_emb=0.0,
-                           layer_idx=0, device=None, dtype=None)
+                           layer_idx=0, device=None, dtype=None, **extra)
         import standalone_hyenadna as S
         init = S._init_weights
     if init_std is not None:
@@ -83,7 +89,8 @@ def main():
         op = build(case, "standalone")
         op_src = build(case, "src")
         op_src.load_state_dict(op.state_dict())
-        if order > 2:
+        if order > 2 or len(spec) > 8:
+            # (options case: standalone_hyenadna.py's filter ignores `normalized` (:192-214), the src module implements it)
             # the two copies of the operator in the reference disagree beyond order 2: standalone_hyenadna.py:283-284
             # orders the filter channels '(o d)', src/models/sequence/hyena.py:408-412 '(v o)'.  The drop-in target is
             # the src module, so the fixture comes from it.
@@ -105,6 +112,9 @@ def main():
         out = {"u": u.numpy(), "dy": dy.numpy(), "y": y.detach().numpy(), "du": u1.grad.numpy(),
                "y64": y64.detach().numpy(), "du64": u64.grad.numpy(),
                "meta": np.array([B, L, D, E, l_max], dtype=np.int64), "w": np.float64(w), "order": np.int64(order)}
+        if len(spec) > 8:
+            import json
+            out["extra_json"] = np.array(json.dumps(spec[8]))
         for k, v in op.state_dict().items():
             out["sd/" + k] = v.numpy()
         for k, p in op.named_parameters():

@@ -1,4 +1,5 @@
 """Helpers to load the committed golden fixtures (tests/golden/*.npz)."""
+import json
 import os
 
 import numpy as np
@@ -7,12 +8,14 @@ import torch
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = ["ref_L64_D8", "ref_L256_D16", "ref_L250_lmax300_D8", "tiny_1k"]      # order = 2
 CASES_ORDER3 = ["ref_order3_L256_D16", "ref_order3_L200_D8"]
+CASES_OPTIONS = ["ref_norm_modlr_L256_D16"]     # normalized=True, modulation_lr != 0, shift != 0
 
 
 def load(case):
     z = np.load(os.path.join(GOLDEN_DIR, case + ".npz"))
     B, L, D, E, l_max = [int(x) for x in z["meta"]]
     out = {"B": B, "L": L, "D": D, "E": E, "l_max": l_max, "w": float(z["w"])}
+    out["extra"] = json.loads(str(z["extra_json"])) if "extra_json" in z.files else {}
     out["sd"] = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
     out["grad"] = {k[5:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("grad/")}
     out["grad64"] = {k[7:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("grad64/")}

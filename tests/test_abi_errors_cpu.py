@@ -56,7 +56,7 @@ def test_workspace_sizing_is_consistent():
 def test_module_rejects_options_outside_the_hot_path():
     import hyena_dna_b200 as H
     for kw in (dict(order=1), dict(num_heads=2), dict(dropout=0.1), dict(activation="gelu"), dict(outer_mixing=True),
-               dict(bidirectional=True), dict(filter_order=16), dict(short_filter_order=4)):
+               dict(linear_mixer=True), dict(filter_order=16), dict(short_filter_order=4)):
         with pytest.raises(H.HyenaB200Error):
             H.HyenaOperator(8, 64, **kw)
     # accepted-and-ignored factory kwargs (long_conv_lm.py:88-95)
@@ -65,6 +65,10 @@ def test_module_rejects_options_outside_the_hot_path():
     assert isinstance(op.filter_fn.pos_emb.z, __import__("torch").nn.Parameter)     # class default lr_pos_emb=1e-5
     op0 = H.HyenaOperator(8, 64, emb_dim=3, lr_pos_emb=0.0)
     assert "filter_fn.pos_emb.z" in dict(op0.named_buffers())
+    # filter options that are built (round 2): normalized, bidirectional, trainable modulation deltas
+    op1 = H.HyenaOperator(8, 64, emb_dim=3, normalized=True, bidirectional=True, modulation_lr=1e-3)
+    assert op1.filter_fn.normalized and op1.filter_fn.bidirectional
+    assert op1.filter_fn.modulation.deltas._optim == {"lr": 1e-3, "weight_decay": 0.0}
 
 
 def test_block_glue_option_guards_and_state_dict_keys():

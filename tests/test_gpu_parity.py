@@ -8,7 +8,8 @@ import pytest
 import torch
 
 from oracle import hyena_oracle as O
-from tests.golden_util import CASES, load
+from tests import parity_util as PU
+from tests.golden_util import CASES, CASES_OPTIONS, load
 
 pytestmark = pytest.mark.gpu
 
@@ -176,6 +177,26 @@ def test_operator_matches_reference_golden(case):
     got = dict(op.named_parameters())
     for name, gref in G["grad"].items():
         _close(got[name].grad, gref, f"{case} grad {name}", rtol=2e-3, atol=2e-5)
+
+
+@pytest.mark.parametrize("case", CASES_OPTIONS)
+def test_operator_filter_options_match_reference_golden(case):
+    """normalized=True (hyena.py:235-236) and trainable modulation deltas (modulation_lr != 0, hyena.py:145-150), non-zero
+    shift: fixture from the unmodified src module (tests/golden/make_golden.py); the deltas gradient is checked too."""
+    dev = _dev()
+    G = load(case)
+    op = _module_from_sd(G["sd"], G["D"], G["l_max"], G["E"], G["w"], dev, **G["extra"])
+    assert isinstance(op.filter_fn.modulation.deltas, torch.nn.Parameter)
+    assert op.filter_fn.modulation.deltas._optim["lr"] == G["extra"]["modulation_lr"]
+    u = G["u"].to(dev).requires_grad_(True)
+    y = op(u)
+    y.backward(G["dy"].to(dev))
+    PU.check(y, G["y"], f"{case} y", ref64=G["y64"])
+    PU.check(u.grad, G["du"], f"{case} du", ref64=G["du64"])
+    got = dict(op.named_parameters())
+    assert "filter_fn.modulation.deltas" in G["grad"]
+    for name, gref in G["grad"].items():
+        PU.check(got[name].grad, gref, f"{case} grad {name}", ref64=G["grad64"][name], param_grad=True)
 
 
 @pytest.mark.parametrize("B,L,D,l_max", [(2, 1001, 8, 1001), (1, 5000, 16, 8192), (2, 32768, 16, 32768),
@@ -604,3 +625,64 @@ def test_checkpointed_stack_reuses_filter_and_matches_plain_autograd():
     assert "filter_tc_fwd" in prof2
     plan = H.memory_plan(1, 1 << 20, 256, 8)
     assert plan["total"] < 180e9
+
+
+# ------------------------------------------------------------------------------------------ fftconv variants (S8 f4)
+@pytest.mark.parametrize("name", ["krev_L100", "krev_L257", "bidir_L128", "bidir_L101"])
+def test_fftconv_k_rev_and_bidirectional_match_reference_golden(name):
+    """k_rev (src/ops/fftconv.py:66-67, hyena.py:63-65) and bidirectional (hyena.py:67-73): fixtures from the unmodified
+    reference fftconv_ref (tests/golden/make_golden_fftconv.py), forward and all gradients, fp64 truth alongside."""
+    import os
+    import numpy as np
+    import hyena_dna_b200 as H
+    dev = _dev()
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fftconv_variants.npz"))
+    T = lambda k: torch.from_numpy(z[f"{name}/{k}"])
+    B, Hh, L, with_rev, bidir = (int(v) for v in z[f"{name}/cfg"])
+    u = T("u").to(dev).requires_grad_(True); k = T("k").to(dev).requires_grad_(True); D = T("D").to(dev).requires_grad_(True)
+    kr = T("krev").to(dev).requires_grad_(True) if with_rev else None
+    n0 = H.launch_count()
+    y = H.fftconv_ref(u, k, D, None, gelu=False, k_rev=kr, bidirectional=bool(bidir))
+    y.backward(T("dy").to(dev))
+    assert H.launch_count() > n0
+    PU.check(y, T("y"), f"{name} y", ref64=T("y64"))
+    PU.check(u.grad, T("du"), f"{name} du", ref64=T("du64"))
+    PU.check(k.grad, T("dk"), f"{name} dk", ref64=T("dk64"), param_grad=True)
+    PU.check(D.grad, T("dD"), f"{name} dD", ref64=T("dD64"), param_grad=True)
+    if with_rev:
+        PU.check(kr.grad, T("dkrev"), f"{name} dk_rev", ref64=T("dkrev64"), param_grad=True)
+        # the same through the op-level entry point of src/ops/fftconv.py:105-108
+        y2 = H.fftconv_func(u.detach(), k.detach(), D.detach(), gelu=False, k_rev=kr.detach())
+        PU.check(y2, T("y"), f"{name} fftconv_func y", ref64=T("y64"))
+    with pytest.raises(H.HyenaB200Error):
+        H.fftconv_ref(u, k, D, None, gelu=False, k_rev=k, bidirectional=True)
+
+
+def test_bidirectional_filter_module_matches_oracle_fp64():
+    """HyenaFilter(bidirectional=True) inside the operator (hyena.py:261 passes the flag to fftconv_ref): the operator runs the
+    chained path with the delayed convolution; checked against an fp64 restatement built from the reference's formula."""
+    dev = _dev()
+    B, L, D = 2, 300, 8
+    g = torch.Generator().manual_seed(11)
+    P = O.init_params(D, L, emb_dim=5, w=10.0, generator=g, init_std=0.02)
+    sd = dict(P)
+    for extra in ("filter_fn.implicit_filter.3.freq", "filter_fn.implicit_filter.5.freq"):
+        sd[extra] = sd["filter_fn.implicit_filter.1.freq"]
+    op = _module_from_sd(sd, D, L, 5, 10.0, dev, bidirectional=True)
+    u = torch.randn(B, L, D, generator=g)
+    y = op(u.to(dev))
+    # fp64 truth: the reference operator's formula with the bidirectional fftconv_ref restated (hyena.py:59-88)
+    P64 = O.to_dtype(P, torch.float64)
+    import torch.nn.functional as F
+    p = F.linear(u.double(), P64["in_proj.weight"], P64["in_proj.bias"]).transpose(1, 2)
+    uc = O.short_filter(p, P64["short_filter.weight"], P64["short_filter.bias"], L)
+    x0, x1, v = uc.split(D, dim=1)
+    k = O.hyena_filter(L, P64)[0].transpose(0, 1)
+    gte = v * x1
+    n = 2 * L
+    pad_before = (L + 2 * (L // 2)) // 2 - L // 2
+    pad_after = L + 2 * (L // 2) - L - pad_before
+    gf = torch.fft.rfft(F.pad(gte, (pad_before, pad_after)), n=n)
+    yc = torch.fft.irfft(gf * (torch.fft.rfft(k, n=n) / n), n=n, norm="forward")[..., :L] + gte * P64["filter_fn.bias"][:, None]
+    y64 = F.linear((yc * x0).transpose(1, 2), P64["out_proj.weight"], P64["out_proj.bias"])
+    PU.check(y, y64.float(), "bidirectional operator y", ref64=y64)

@@ -3,7 +3,7 @@ import pytest
 import torch
 
 from oracle import hyena_oracle as O
-from tests.golden_util import CASES, CASES_ORDER3, load
+from tests.golden_util import CASES, CASES_OPTIONS, CASES_ORDER3, load
 
 
 @pytest.mark.parametrize("case", CASES + CASES_ORDER3)
@@ -27,6 +27,23 @@ def test_oracle_fp64_matches_reference_fp64(case):
     y, du, _ = O.operator_fwd_bwd(G["u"].double(), P, G["dy"].double())
     torch.testing.assert_close(y, G["y64"], rtol=1e-10, atol=1e-12)
     torch.testing.assert_close(du, G["du64"], rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("case", CASES_OPTIONS)
+def test_oracle_filter_options_match_reference(case):
+    """normalized=True, modulation_lr != 0 (deltas gradient), shift != 0: fixture from the unmodified src module."""
+    G = load(case)
+    P = O.canonical(G["sd"])
+    names = [k for k in P if k not in ("filter_fn.pos_emb.z", "filter_fn.pos_emb.t")]
+    y, du, grads = O.operator_fwd_bwd(G["u"], P, G["dy"], shift=G["extra"]["shift"], grads_for=names,
+                                      normalized=G["extra"]["normalized"])
+    torch.testing.assert_close(y, G["y"], rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(du, G["du"], rtol=1e-5, atol=1e-6)
+    assert "filter_fn.modulation.deltas" in G["grad"]
+    for k, g in G["grad"].items():
+        kk = "filter_fn.implicit_filter.1.freq" if k.endswith(".freq") else k
+        scale = float(g.abs().max()) + 1e-30
+        assert float((grads[kk] - g).abs().max()) <= 2e-5 * scale + 1e-7, k
 
 
 def test_positional_embedding_and_deltas_match_reference_buffers():
