@@ -222,38 +222,6 @@ struct PipeRun {
   ~PipeRun() { if (active) { g_prof_suppress = false; for (int i = 0; i < S; ++i) { cudaEventRecord(p->join[i], p->st[i]); cudaStreamWaitEvent(main, p->join[i], 0); } } }
 };
 
-// Experimental (HYENA_B200_L2_PERSIST=1): mark the FFT scratch as L2-persisting for the duration of a call so that, with
-// a launch group small enough to fit (HYENA_B200_GROUP_MB <= ~64), the inter-pass intermediate stays on chip.
-struct L2Persist {
-  cudaStream_t s = nullptr;
-  bool on = false;
-  void begin(cudaStream_t stream, void* ws, size_t bytes) {
-    static const bool want = getenv("HYENA_B200_L2_PERSIST") && !strcmp(getenv("HYENA_B200_L2_PERSIST"), "1");
-    if (!want) return;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceProp p;
-    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess || p.persistingL2CacheMaxSize <= 0) return;
-    size_t lim = (size_t)p.persistingL2CacheMaxSize;
-    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, lim);
-    size_t win = bytes < (size_t)p.accessPolicyMaxWindowSize ? bytes : (size_t)p.accessPolicyMaxWindowSize;
-    cudaStreamAttrValue v;
-    memset(&v, 0, sizeof(v));
-    v.accessPolicyWindow.base_ptr = ws;
-    v.accessPolicyWindow.num_bytes = win;
-    v.accessPolicyWindow.hitRatio = win <= lim ? 1.0f : (float)lim / (float)win;
-    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    if (cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v) == cudaSuccess) { s = stream; on = true; }
-  }
-  ~L2Persist() {
-    if (!on) return;
-    cudaStreamAttrValue v;
-    memset(&v, 0, sizeof(v));
-    cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v);
-  }
-};
-
 static int check_shape(int B, int D, int L) {
   HY_CHECK(B >= 1 && D >= 1 && L >= 1, "bad shape B=%d D=%d L=%d", B, D, L);
   HY_CHECK(L <= (1 << 20), "sequence length %d exceeds the supported maximum %d", L, 1 << 20);
@@ -525,8 +493,6 @@ HY_API int hyena_b200_core_fwd(const float* p, const float* in_bias, const float
   if (get_twiddles(s, &T)) return 1;
   Carve c;
   if (carve(workspace, workspace_bytes, B, D, L, false, &c)) return 1;
-  L2Persist persist;
-  persist.begin(s, workspace, workspace_bytes);
   PassArgs a = base_args(B, D, L, T);
   a.A = c.A; a.kspec = reinterpret_cast<const float2*>(kspec);
   a.p = p; a.in_bias = in_bias; a.sw = sw; a.sb = sb; a.fbias = fbias; a.out = y_pre; a.out2 = c_save;
@@ -572,8 +538,6 @@ HY_API int hyena_b200_core_bwd(const float* dy_pre, const float* p, const float*
   if (get_twiddles(s, &T)) return 1;
   Carve c;
   if (carve(workspace, workspace_bytes, B, D, L, true, &c)) return 1;
-  L2Persist persist;
-  persist.begin(s, workspace, workspace_bytes);
   PassArgs a = base_args(B, D, L, T);
   a.kspec = reinterpret_cast<const float2*>(kspec);
   a.p = p; a.in_bias = in_bias; a.sw = sw; a.sb = sb; a.fbias = fbias;
