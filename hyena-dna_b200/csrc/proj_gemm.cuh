@@ -574,12 +574,12 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a, const 
   }
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      tc::mbar_init(B_FULL(s), 256); tc::mbar_init(B_EMPTY(s), 1);      // both converter groups build the image
+      tc::mbar_init(B_FULL(s), 128); tc::mbar_init(B_EMPTY(s), 1);
       tc::mbar_init(A_FULL(s), 128); tc::mbar_init(A_EMPTY(s), 1);
       tc::mbar_init(DM_FULL(s), 1); tc::mbar_init(DM_EMPTY(s), 128);
     }
     tc::mbar_init(DC_FULL, 1);
-    for (int j = 0; j < kStg; ++j) { tc::mbar_init(S_FULL(j), 1); tc::mbar_init(Y_EMPTY(j), 128); tc::mbar_init(X_EMPTY(j), 256); }
+    for (int j = 0; j < kStg; ++j) { tc::mbar_init(S_FULL(j), 1); tc::mbar_init(Y_EMPTY(j), 128); tc::mbar_init(X_EMPTY(j), 128); }
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -604,52 +604,6 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a, const 
   const long long total_chunks = (long long)a.B * a.chunks_per_b;
   const long long c_begin = total_chunks * split / a.splits, c_end = total_chunks * (split + 1) / a.splits;
   const long long nchunks = c_end - c_begin;
-
-  // ---- X rows -> K-major hi / lo images, shared by the B-side warps and (for load balance) the A-side warps.
-  // Thread t of a 128-thread group converts the pieces (row r, quad kq) with r % 8 == t % 8: the eight lanes of a quarter warp
-  // then write one contiguous 128-byte core matrix (bank-conflict free); 1024 pieces per chunk, piece i of thread t is row
-  // rlo + 8 (rhi0 + 2 i).  The B-side warps take i < kBShare, the A-side warps -- which otherwise sit ~1300 cycles per chunk
-  // waiting for their TMEM buffer -- the rest: one converter warp per scheduler ran the whole image build as a single
-  // latency-bound instruction stream (~2200 cycles per chunk for ~350 instructions, the bottleneck of the kernel).
-  constexpr int kBShare = 5;
-  const int ct = tid & 127;
-  const int rlo = ct & 7, kq = (ct >> 3) & 7, rhi0 = ct >> 6;
-  const bool use_fir = a.fir != nullptr;
-  auto convert_pieces = [&](auto i0_, auto i1_, const unsigned char* st, unsigned char* hi_img, unsigned char* lo_img,
-                            const float (&w)[8][3]) {
-    constexpr int I0 = decltype(i0_)::value, I1 = decltype(i1_)::value;
-#pragma unroll
-    for (int i = I0; i < I1; ++i) {
-      const int r = rlo + 8 * (rhi0 + 2 * i);
-      const float* row = reinterpret_cast<const float*>(st + r * kXPitch) + 4 * kq;
-      float4 v = *reinterpret_cast<const float4*>(row);
-      if (use_fir) {
-        const float2 nx = *reinterpret_cast<const float2*>(row + 4);
-        const float x4 = nx.x, x5 = nx.y;
-        float4 o;
-        o.x = fmaf(w[i][2], v.x, fmaf(w[i][1], v.y, w[i][0] * v.z));
-        o.y = fmaf(w[i][2], v.y, fmaf(w[i][1], v.z, w[i][0] * v.w));
-        o.z = fmaf(w[i][2], v.z, fmaf(w[i][1], v.w, w[i][0] * x4));
-        o.w = fmaf(w[i][2], v.w, fmaf(w[i][1], x4, w[i][0] * x5));
-        v = o;
-      }
-      float4 h, lw;
-      tc::split_tf32(v.x, h.x, lw.x); tc::split_tf32(v.y, h.y, lw.y);
-      tc::split_tf32(v.z, h.z, lw.z); tc::split_tf32(v.w, h.w, lw.w);
-      const uint32_t off = pg::img_off(r, 4 * kq);
-      *reinterpret_cast<float4*>(hi_img + off) = h;
-      *reinterpret_cast<float4*>(lo_img + off) = lw;
-    }
-  };
-  float w[8][3];
-  if (warp < 8) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int m = m0 + rlo + 8 * (rhi0 + 2 * i);
-#pragma unroll
-      for (int j = 0; j < 3; ++j) w[i][j] = (use_fir && m < a.M) ? __ldg(a.fir + 3 * m + j) : 0.f;
-    }
-  }
 
   if (warp < 4) {
     // ---------------------------------------------------------------- A side: thread = column n of Y = TMEM lane
@@ -683,22 +637,25 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a, const 
       tc::tmem_wait_st();
       tc::fence_before_sync();
       tc::mbar_arrive(A_FULL(buf));
-      // ---- this group's share of the X image build (same image buffer index as the A buffer: it & 1)
-      timed_wait(B_EMPTY(buf), ((it >> 1) & 1) ^ 1, 3);
-      {
-        const unsigned char* xs = smem + kOffX + (size_t)ss * kXStage;
-        unsigned char* hi_img = smem + kOffImg + (size_t)buf * 2 * kImg;
-        convert_pieces(IC<kBShare>{}, IC<8>{}, xs, hi_img, hi_img + kImg, w);
-      }
-      tc::mbar_arrive(X_EMPTY(ss));
-      tc::fence_async_smem();
-      tc::mbar_arrive(B_FULL(buf));
     }
     if (dbg_on && tid == 0) { a.dbg[0] = dbg_t[0]; a.dbg[1] = dbg_t[1]; a.dbg[2] = dbg_t[2]; a.dbg[15] = nchunks;
                               a.dbg[14] = clock64() - dbg_start; }
   } else if (warp < 8) {
     // ---------------------------------------------------------------- B side: X rows -> K-major hi / lo images
     const int t = tid - 128;
+    const bool use_fir = a.fir != nullptr;
+    // this thread converts pieces (row r, quad k4) with r % 8 == t % 8: the eight lanes of a quarter warp then write one
+    // contiguous 128-byte core matrix (bank-conflict free); 1024 pieces per chunk, 8 per thread
+    const int rlo = t & 7, kq = (t >> 3) & 7, rhi0 = t >> 6;            // rows r = rlo + 8 * (rhi0 + 2 i), i < 8
+    float w[8][3];
+    if (use_fir) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = m0 + rlo + 8 * (rhi0 + 2 * i);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) w[i][j] = (m < a.M) ? __ldg(a.fir + 3 * m + j) : 0.f;
+      }
+    }
     for (long long q = 0; q < nchunks; ++q) {
       const int ss = (int)(q % kStg);
       {
@@ -712,7 +669,29 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a, const 
       timed_wait(B_EMPTY(s), ((it >> 1) & 1) ^ 1, 0);                   // the MMAs that read this image pair are done
       const long long tV = dbg_on ? clock64() : 0;
       unsigned char* hi_img = smem + kOffImg + (size_t)s * 2 * kImg;
-      convert_pieces(IC<0>{}, IC<kBShare>{}, st, hi_img, hi_img + kImg, w);
+      unsigned char* lo_img = hi_img + kImg;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = rlo + 8 * (rhi0 + 2 * i);
+        const float* row = reinterpret_cast<const float*>(st + r * kXPitch) + 4 * kq;
+        float4 v = *reinterpret_cast<const float4*>(row);
+        if (use_fir) {
+          const float2 nx = *reinterpret_cast<const float2*>(row + 4);
+          const float x4 = nx.x, x5 = nx.y;
+          float4 o;
+          o.x = fmaf(w[i][2], v.x, fmaf(w[i][1], v.y, w[i][0] * v.z));
+          o.y = fmaf(w[i][2], v.y, fmaf(w[i][1], v.z, w[i][0] * v.w));
+          o.z = fmaf(w[i][2], v.z, fmaf(w[i][1], v.w, w[i][0] * x4));
+          o.w = fmaf(w[i][2], v.w, fmaf(w[i][1], x4, w[i][0] * x5));
+          v = o;
+        }
+        float4 h, lw;
+        tc::split_tf32(v.x, h.x, lw.x); tc::split_tf32(v.y, h.y, lw.y);
+        tc::split_tf32(v.z, h.z, lw.z); tc::split_tf32(v.w, h.w, lw.w);
+        const uint32_t off = pg::img_off(r, 4 * kq);
+        *reinterpret_cast<float4*>(hi_img + off) = h;
+        *reinterpret_cast<float4*>(lo_img + off) = lw;
+      }
       tc::mbar_arrive(X_EMPTY(ss));                                     // staged rows consumed
       tc::fence_async_smem();
       tc::mbar_arrive(B_FULL(s));

@@ -172,6 +172,15 @@ __device__ __forceinline__ void mbar_wait_u(uint32_t mbar, uint32_t parity) {
   uint32_t done = 0;
   const long long t0 = clock64();
   while (!done) {
+#if defined(HY_WAIT_HINT_NS) && HY_WAIT_HINT_NS > 0
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(mbar), "r"(parity), "r"((uint32_t)HY_WAIT_HINT_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -179,6 +188,7 @@ __device__ __forceinline__ void mbar_wait_u(uint32_t mbar, uint32_t parity) {
         : "=r"(done)
         : "r"(mbar), "r"(parity)
         : "memory");
+#endif
     if (!done && clock64() - t0 > 4000000000LL) __trap();
   }
 }
