@@ -108,6 +108,7 @@ cudaError_t launch_proj_gemm(const float* act, int act_layout, const float* W, i
   pg::Args a;
   a.act = act; a.wimg = wimg; a.out = out; a.bias = bias; a.fir = fir;
   a.dbg = g_proj_dbg;
+  a.zero = 0;
   a.B = B; a.L = L; a.K = K; a.N = N; a.l0 = l0; a.ln = ln;
   // TMA needs 16-byte aligned rows (global stride a multiple of 16 bytes) and, for the channel-major box, a 16-byte
   // aligned first position
@@ -142,7 +143,7 @@ cudaError_t launch_proj_wgrad(const float* X, const float* Y, const float* fir, 
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   wg::Args a;
-  a.X = X; a.Y = Y; a.fir = fir; a.part = part; a.dbg = g_proj_dbg; a.B = B; a.L = L; a.M = M; a.N = N;
+  a.X = X; a.Y = Y; a.fir = fir; a.part = part; a.dbg = g_proj_dbg; a.zero = 0; a.B = B; a.L = L; a.M = M; a.N = N;
   a.chunks_per_b = (L + 31) / 32;
   proj_wgrad_plan(M, N, sms, &a.mtiles, &a.ntiles, &a.splits);
   const long long total_chunks = (long long)B * a.chunks_per_b;

@@ -63,6 +63,7 @@ struct Args {
   int ntiles_n;          // ceil(N / NT)
   int mtiles_per_b;      // ceil(ln / 128)
   int vec;               // 1: the activation qualifies for TMA (16-byte aligned rows): `tmap` is valid
+  unsigned zero;         // 0 at run time (tc::mbar_arrive_after_loads)
   long long* dbg;        // optional (tools/dbg_proj_timing.py): per-role wait / work cycle counters of CTA 0, or null
 };
 
@@ -232,7 +233,12 @@ __global__ void __launch_bounds__(kThreads, 1) proj_gemm_kernel(const Args a, co
             }
           }
         }
-        tc::mbar_arrive(S_EMPTY(s));                               // staging slot read: the producer may refill it
+        {                                                          // staging slot read: the producer may refill it -- once the
+          uint32_t dep = 0;                                        // loads have actually returned (see mbar_arrive_after_loads)
+#pragma unroll
+          for (int j = 0; j < kKC; ++j) dep |= __float_as_uint(x[j]);
+          tc::mbar_arrive_after_loads(S_EMPTY(s), dep, a.zero);
+        }
         uint32_t hi[kKC], lo[kKC];
 #pragma unroll
         for (int j = 0; j < kKC; ++j) {
@@ -537,6 +543,7 @@ struct Args {
   int chunks_per_b;     // ceil(L / 32)
   int mtiles, ntiles, splits;
   int vec;              // 1: both tensors qualify for TMA (16-byte aligned rows): the tensor maps are valid
+  unsigned zero;        // 0 at run time (tc::mbar_arrive_after_loads)
 };
 
 // Staging: one producer thread issues, per chunk of 32 positions, ONE tiled TMA copy of the Y tile (box 128 n x 32 pos of
@@ -625,7 +632,12 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Args a, const 
         tc::split_tf32(v, h, lw);
         hi[k] = __float_as_uint(h); lo[k] = __float_as_uint(lw);
       }
-      tc::mbar_arrive(Y_EMPTY(ss));                                     // staged tile consumed: the producer may refill the slot
+      {                                                                 // staged tile consumed (loads returned): the producer may
+        uint32_t dep = 0;                                               // refill the slot
+#pragma unroll
+        for (int k = 0; k < 32; ++k) dep |= hi[k];
+        tc::mbar_arrive_after_loads(Y_EMPTY(ss), dep, a.zero);
+      }
       const uint32_t it = (uint32_t)q;
       const int buf = it & 1;
       if (dbg_on) dbg_t[2] += clock64() - tC;

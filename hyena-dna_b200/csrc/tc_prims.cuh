@@ -139,6 +139,16 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
 }
+// Release of a shared-memory slot whose contents this thread has just LOADED into registers: the arrive must not be performed
+// before those loads have returned.  A plain arrive is issued right behind the LDS instructions (no register dependency) and is
+// handled by the barrier unit, not queued behind them in the load pipe -- measured: with the refilling TMA copy issued as soon
+// as the barrier completes, ~1e-6 of the runs read rows the copy engine had already overwritten (tools/determinism_proj.py).
+// `dep` must be computed from every loaded register; `zero` is a run-time 0 the assembler cannot fold, so the arrive count
+// (always 1) carries a true data dependency on the loads.
+__device__ __forceinline__ void mbar_arrive_after_loads(uint32_t mbar, uint32_t dep, uint32_t zero) {
+  const uint32_t cnt = 1u + (dep & zero);
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(cnt) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
 }
