@@ -14,11 +14,19 @@ for (B, L, D) in [(2, 1024, 8), (1, 3000, 8), (1, 40000, 4)]:
     y = op(u); y.backward(torch.randn_like(y))
     uu = torch.randn(B, 3, L, device=dev, requires_grad=True); k = torch.randn(3, L, device=dev, requires_grad=True)
     Dv = torch.randn(3, device=dev, requires_grad=True)
-    o = H.fftconv_func(uu, k, Dv, gelu=False); o.backward(torch.randn_like(o))
+    o = H.fftconv_func(uu, k, Dv, gelu=False, k_rev=k.detach().flip(-1)); o.backward(torch.randn_like(o))
+# filter options, order 3, block glue (round 2)
+from functools import partial
+op = H.HyenaOperator(8, 512, order=3, emb_dim=5, normalized=True, modulation_lr=1e-3, lr_pos_emb=0.0).to(dev)
+y = op(torch.randn(2, 512, 8, device=dev, requires_grad=True)); y.sum().backward()
+bb = H.Backbone(16, 2, partial(H.HyenaOperator, l_max=256, emb_dim=5, lr_pos_emb=0.0)).to(dev)
+x = torch.randn(2, 256, 16, device=dev, requires_grad=True); bb(x).square().sum().backward()
+x = torch.randn(300, 50, device=dev, requires_grad=True); w = torch.randn(50, device=dev, requires_grad=True)
+yy, rr = H.ops.add_layer_norm(x, None, w, None, 1e-5); (yy.sum() + rr.sum()).backward()
 torch.cuda.synchronize(); print("ok")
 PY
-for tool in memcheck racecheck synccheck; do
+for tool in memcheck synccheck racecheck; do
   echo "== $tool"
-  timeout 900 compute-sanitizer --tool $tool --print-limit 5 python /tmp/san_case.py > gpurun_out/sanitizer_$tool.log 2>&1
+  timeout 420 compute-sanitizer --tool $tool --print-limit 5 python /tmp/san_case.py > gpurun_out/sanitizer_$tool.log 2>&1
   tail -4 gpurun_out/sanitizer_$tool.log
 done
