@@ -194,11 +194,19 @@ struct ColGeo {
   static constexpr size_t STAGE_FWD = TWO ? (size_t)DATA_ROWS * (WP + WP) * sizeof(float) : 0;
   static constexpr size_t BATCH_FWD_FLOATS = (size_t)SB_FWD * R2 * WP;       // x0 windows only
   static constexpr size_t BATCH_BWD_FLOATS = (size_t)SB_BWD * R2 * (3 * WP + 2 * XP);
-  // the forward epilogue is double buffered, the (larger) backward batches are not (measured: 8 half-size
-  // double-buffered batches were 2x slower than 4 full-size single-buffered ones)
-  static constexpr size_t STAGE_INV = TWO ? (2 * BATCH_FWD_FLOATS > BATCH_BWD_FLOATS ? 2 * BATCH_FWD_FLOATS : BATCH_BWD_FLOATS) * sizeof(float) : 0;
+  // both epilogues are double buffered: the cp.async group of batch k+1 is in flight while batch k is consumed.  (Round 1 kept the
+  // larger backward batches single buffered: eight HALF-size double-buffered batches in the same shared memory had been 2x slower;
+  // with two full-size buffers -- 94 KB per CTA, two CTAs per SM still fit -- col_inv<bwd_dg> went 2.56 -> 2.36 ms.)
+  // Shared memory per mode: the forward kernel keeps its smaller footprint.
+  template <int MODE>
+  static constexpr size_t stage_inv() {
+    return TWO ? 2 * (MODE == INV_BWD_DG ? BATCH_BWD_FLOATS : BATCH_FWD_FLOATS) * sizeof(float) : 0;
+  }
+  template <int MODE>
+  static constexpr size_t smem_inv() {
+    return (MODE == INV_BWD_DG || MODE == INV_CONV_FWD) && stage_inv<MODE>() > EXCH ? stage_inv<MODE>() : EXCH;
+  }
   static constexpr size_t SMEM_FWD = EXCH > STAGE_FWD ? EXCH : STAGE_FWD;
-  static constexpr size_t SMEM_INV = EXCH > STAGE_INV ? EXCH : STAGE_INV;
   static constexpr size_t SMEM = EXCH;
   static_assert(C <= M2, "column tile wider than a row");
 };
@@ -470,7 +478,7 @@ __device__ __forceinline__ void col_inv_body(const PassArgs& a, const int bx, co
     if ((MODE == INV_CONV_FWD || MODE == INV_BWD_DG) && a.stage) {
       // epilogue operands staged through shared memory, SB slots (SB*R2 consecutive rows) per batch; forward:
       // double buffered, the cp.async group of batch k+1 is in flight while batch k is consumed
-      constexpr bool DBL = (MODE == INV_CONV_FWD);
+      constexpr bool DBL = true;
       constexpr int SB = (MODE == INV_BWD_DG) ? CG::SB_BWD : CG::SB_FWD;
       constexpr int NBATCH = 16 / SB;
       constexpr int BROWS = SB * CG::R2;
