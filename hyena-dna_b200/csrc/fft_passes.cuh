@@ -978,6 +978,71 @@ __device__ __forceinline__ void row_bwd1_staged_body(const PassArgs& a, const in
   row_ifft_store<LOGM2>(v, ex, Krow_out, q, id.k1, logM, a.T, rsync);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Forward row pass with the filter spectrum row staged by cp.async under the forward row FFT (the register form issues 64
+// __ldg per thread right in front of the pointwise product: long_scoreboard is its top stall).  128-thread CTAs of four
+// rows, shared memory rows * (EX + M2) complex = 66.6 KB: three CTAs per SM.  Default (2.13 -> 1.98 ms at large-1m,
+// profiles/r2_ab.txt run E; a 256-thread staged form with 131 KB per CTA had lost in round 2's first sweep);
+// HYENA_B200_ROW_FWD_STAGE=0 selects the register-load form.
+// ------------------------------------------------------------------------------------------------
+template <int LOGM2>
+__host__ __device__ constexpr size_t row_fwd_staged_smem_elems(int rows) {
+  return (size_t)rows * (RowGeo<LOGM2>::EX + RowGeo<LOGM2>::M2);
+}
+
+template <int LOGM2>
+__device__ __forceinline__ void row_fwd_staged_body(const PassArgs& a, const int bx, const int by, unsigned char* smem_raw) {
+  using RG = RowGeo<LOGM2>;
+  constexpr int M2 = RG::M2, TPR = RG::TPR;
+  float2* smem = reinterpret_cast<float2*>(smem_raw);
+  const int M1 = 1 << a.logM1;
+  const int logM = a.logM1 + LOGM2;
+  const int slot = threadIdx.x / TPR, q = threadIdx.x % TPR;
+  const int nslots = blockDim.x / TPR;
+  const RowIds id = row_ids(M1, nslots, bx, slot);
+  const size_t rowElems = (size_t)M1 * M2;
+  const RowSync<LOGM2> rsync{1 + slot};
+  float2* ex = smem + slot * RG::EX;
+  const float2* exp_ = smem + id.pslot * RG::EX;
+  float2* kg = smem + nslots * RG::EX + slot * M2;
+  const float2* kgp = smem + nslots * RG::EX + id.pslot * M2;
+
+  const int r = by;
+  const int ci = r / a.B, c = a.c0 + ci;
+  float2* Arow = a.A + (size_t)r * rowElems + (size_t)id.k1 * M2;
+  const float2* Krow = a.kspec + (size_t)c * rowElems + (size_t)id.k1 * M2;
+#pragma unroll
+  for (int i = 0; i < M2 / 2 / TPR; ++i) {                           // 8 KB = 512 x 16 B, 16 per lane, coalesced
+    const int e = 2 * (TPR * i + q);
+    cp_async16(kg + e, Krow + e, true);
+  }
+  cp_async_commit();
+  const float2 wbase = root20(a.T, ((uint32_t)id.k1 + ((uint32_t)q << a.logM1)) << (20 - logM));
+  const float fb2 = a.fbias ? 2.f * __ldg(a.fbias + c) : 0.f;
+  row_fft_to_smem<LOGM2>(Arow, ex, ex, q, a.T, rsync);
+  if (a.gspec) {                                                     // keep the spectrum of g for the backward pass
+    float2* G = a.gspec + ((size_t)ci * a.B + (r - ci * a.B) + (size_t)a.c0 * a.B) * rowElems + (size_t)id.k1 * M2;
+    static_for<0, 32>([&](auto s_) { constexpr int s = decltype(s_)::value; G[TPR * s + q] = ex[TPR * s + q]; });
+  }
+  cp_async_wait_group<0>();
+  __syncthreads();                                                   // own + partner: spectrum and k row visible
+  float2 v[32];
+  static_for<0, 32>([&](auto s_) {
+    constexpr int s = decltype(s_)::value;
+    const int k2 = TPR * s + q;
+    const int pc = (M2 - k2 - id.nz) & (M2 - 1);
+    float2 E, O, He, Ho;
+    even_odd(ex[k2], cconj(exp_[pc]), E, O);
+    even_odd_filter(kg[k2], cconj(kgp[pc]), fb2, He, Ho);
+    const float2 W = mul_w32<s, false>(wbase);
+    float2 Ye = cadd(cmul(E, He), cmul(W, cmul(O, Ho)));
+    float2 Yo = cadd(cmul(E, Ho), cmul(O, He));
+    v[s] = cadd(Ye, cmul_i(Yo));
+  });
+  __syncthreads();                                                   // partner rows are done reading this row's spectrum
+  row_ifft_store<LOGM2>(v, ex, Arow, q, id.k1, logM, a.T, rsync);
+}
+
 template <int MODE, int LOGM2>
 __global__ void __launch_bounds__(MODE == ROW_CONV_BWD1 ? 128 : 256, MODE == ROW_CONV_BWD ? 1 : (MODE == ROW_CONV_BWD1 ? 3 : 2))
 row_pass_kernel(const PassArgs a) {
