@@ -120,19 +120,61 @@ def hyena_filter(L, P, shift=0.0, modulate=True, normalized=False):
 
 
 # ----------------------------------------------------------------------------- fftconv
-def fftconv_ref(u, k, D):
+def fftconv_ref(u, k, D, k_rev=None, bidirectional=False):
     """y = irfft(rfft(u, 2L) * rfft(k, 2L)/2L, norm='forward')[:L] + u * D[:, None].
 
-    src/models/sequence/hyena.py:59-88 with gelu=False, dropout_mask=None, k_rev=None,
-    bidirectional=False (the HyenaFilter.forward call at :261); identical to
-    src/ops/fftconv.py:15-34 and standalone_hyenadna.py:45-60.  u (..., H, L), k (H, L), D (H,).
+    src/models/sequence/hyena.py:59-88 with gelu=False, dropout_mask=None (the HyenaFilter.forward call at :261);
+    without k_rev / bidirectional identical to src/ops/fftconv.py:15-34 and standalone_hyenadna.py:45-60.
+    k_rev (:63-65): second filter whose conjugated spectrum is added (an anticausal half).  bidirectional (:67-73): the input
+    is padded by ~L/2 on both sides (to exactly the 2L transform points) before the cyclic product.
+    u (..., H, L), k (H, L), D (H,).
     """
     L = u.shape[-1]
     n = 2 * L
     k_f = torch.fft.rfft(k, n=n) / n
-    u_f = torch.fft.rfft(u.to(k.dtype), n=n)
+    if k_rev is not None:
+        k_f = k_f + (torch.fft.rfft(k_rev, n=n) / n).conj()
+    if bidirectional:
+        padded_length = L + 2 * (L // 2)
+        pad_before = padded_length // 2 - (L // 2)
+        pad_after = padded_length - L - pad_before
+        u_f = torch.fft.rfft(F.pad(u.to(k.dtype), (pad_before, pad_after)), n=n)
+    else:
+        u_f = torch.fft.rfft(u.to(k.dtype), n=n)
     y = torch.fft.irfft(u_f * k_f, n=n, norm="forward")[..., :L]
     return (y + u * D.unsqueeze(-1)).to(u.dtype)
+
+
+def fftconv_variants_time_domain(u, k, D, k_rev=None, bidirectional=False):
+    """The same two options stated in the time domain -- the decomposition hyena_dna_b200.fftconv uses to run them on the
+    causal-convolution / correlation kernels (tests/test_variants_model_cpu.py checks it against fftconv_ref above):
+      k_rev:          y[t] += sum_{s >= t} u[s] k_rev[s - t]                                   (a correlation)
+      bidirectional:  y[t]  = c[t - pad_before] (causal conv c delayed, zeros shifted in)
+                              + sum_m u[t + m] r[m],  r[m] = k[2L - pad_before - m] for L - pad_before < m < L   (the wrapped taps)
+    O(L^2); float64, small L only."""
+    L = u.shape[-1]
+    conv = torch.zeros_like(u)
+    for j in range(L):
+        conv[..., j:] += k[..., j, None] * u[..., : L - j]
+
+    def corr(x, f):
+        out = torch.zeros_like(x)
+        for m in range(L):
+            out[..., : L - m] += f[..., m, None] * x[..., m:]
+        return out
+    if bidirectional:
+        assert k_rev is None
+        pad = (L + 2 * (L // 2)) // 2 - L // 2
+        y = F.pad(conv[..., : L - pad], (pad, 0)) if pad < L else torch.zeros_like(conv)
+        r = torch.zeros_like(k)
+        if pad > 1:
+            r[..., L - pad + 1:] = k[..., L - pad + 1:].flip(-1)
+        y = y + corr(u, r)
+    else:
+        y = conv
+        if k_rev is not None:
+            y = y + corr(u, k_rev)
+    return y + u * D.unsqueeze(-1)
 
 
 def fftconv_direct(u, k, D):
