@@ -260,3 +260,31 @@ def reference_fftconv_protocol(fftconv_fwd, fftconv_bwd, u, k, D, dout):
                                      fft_size, False, False)
     dk = torch.fft.irfft(dk_f, n=fft_size, norm='forward')[..., :seqlen]
     return out, du, dk, dD
+
+
+# ----------------------------------------------------------------------------- block glue
+def prenorm_backbone(x, sd, n_layer, shift=0.0, eps=1e-5, residual_in_fp32=True):
+    """Stack of pre-norm Blocks + final norm, restated from flash-attention/flash_attn/modules/block.py:111-148 (prenorm
+    branch, dropout p = 0, residual_in_fp32) and src/models/sequence/long_conv_lm.py:383-396:
+        residual = hidden + residual;  hidden = mixer(LN1(residual));
+        [if the block has an MLP]  residual = hidden + residual;  hidden = fc2(gelu_tanh(fc1(LN2(residual))))
+        out = ln_f(hidden + residual)
+    sd: state_dict with the reference's keys (layers.N.{mixer.*, norm1.*, mlp.fc1/fc2.*, norm2.*}, ln_f.*)."""
+    D = x.shape[-1]
+    hidden, residual = x, None
+    for i in range(n_layer):
+        pre = f"layers.{i}."
+        residual = hidden + residual if residual is not None else hidden
+        h = F.layer_norm(residual, (D,), sd[pre + "norm1.weight"], sd[pre + "norm1.bias"], eps)
+        if residual_in_fp32:                       # block.py:118-119: the residual STREAM is rounded to fp32 (a no-op in fp32 runs)
+            residual = residual.to(torch.float32)
+        P = canonical({k[len(pre + "mixer."):]: v for k, v in sd.items() if k.startswith(pre + "mixer.")})
+        hidden = hyena_operator(h, P, shift)
+        if pre + "mlp.fc1.weight" in sd:
+            residual = hidden + residual
+            h = F.layer_norm(residual, (D,), sd[pre + "norm2.weight"], sd[pre + "norm2.bias"], eps)
+            if residual_in_fp32:
+                residual = residual.to(torch.float32)
+            h = F.gelu(F.linear(h, sd[pre + "mlp.fc1.weight"], sd[pre + "mlp.fc1.bias"]), approximate="tanh")
+            hidden = F.linear(h, sd[pre + "mlp.fc2.weight"], sd[pre + "mlp.fc2.bias"])
+    return F.layer_norm(hidden + residual, (D,), sd["ln_f.weight"], sd["ln_f.bias"], eps)

@@ -79,3 +79,26 @@ def test_causality():
     u2 = u.clone(); u2[:, 40:] += 1.0
     y1 = O.hyena_operator(u2, P)
     torch.testing.assert_close(y0[:, :40], y1[:, :40], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("case", ["block_L128_D32_mlp", "block_L96_D16_nomlp"])
+def test_oracle_prenorm_backbone_matches_reference_block(case):
+    """Block glue (S8 f1): the oracle's restatement against fixtures from the unmodified flash_attn Block + HyenaOperator + Mlp
+    (tests/golden/make_golden_block.py), forward, input gradient and every parameter gradient, fp32 and fp64."""
+    import os
+    import numpy as np
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", case + ".npz"))
+    for dt, tag, tol in ((torch.float32, "", 3e-5), (torch.float64, "64", 1e-9)):
+        sd = {k[3:]: torch.from_numpy(z[k]).to(dt) for k in z.files if k.startswith("sd/")}
+        want = [k[5:] for k in z.files if k.startswith("grad/")]
+        for k in want:
+            sd[k].requires_grad_(True)
+        x = torch.from_numpy(z["x"]).to(dt).requires_grad_(True)
+        y = O.prenorm_backbone(x, sd, 2)
+        y.backward(torch.from_numpy(z["dy"]).to(dt))
+        assert float((y.detach() - torch.from_numpy(z["y" + tag])).abs().max()) <= tol * max(1.0, float(np.abs(z["y" + tag]).max()))
+        assert float((x.grad - torch.from_numpy(z["dx" + tag])).abs().max()) <= tol * max(1.0, float(np.abs(z["dx" + tag]).max()))
+        for k in want:                          # named_parameters() of the reference lists the shared freq tensor once (.1.freq)
+            ref = torch.from_numpy(z[("grad64/" if tag else "grad/") + k])
+            assert sd[k].grad is not None, k
+            assert float((sd[k].grad - ref).abs().max()) <= 10 * tol * max(1.0, float(ref.abs().max())), k
